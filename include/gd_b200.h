@@ -1,0 +1,195 @@
+/*
+ * gd_b200.h — C-ABI of the B200 (sm_100a) gesture-DDPM sampling kernels.
+ *
+ * The reference (wubowen416/Speech-driven-Gesture-Generation-...) is pure Python and has no
+ * FFI of its own; the boundary a maintainer binds is therefore the set of torch ops its hot
+ * loop issues.  Each entry point below names the reference call site it replaces
+ * (paths relative to the reference repo root).  All pointers are raw CUDA device pointers
+ * unless stated otherwise, `stream` is a `cudaStream_t` passed as `void*`, every function
+ * returns 0 on success or a negative gd_status and records a message readable through
+ * gd_last_error().  Nothing here allocates device memory or synchronises the device; the
+ * caller owns every buffer.  Not thread-safe per stream.
+ *
+ * Conventions
+ *   - activations are row-major "token rows": row = clip * tokens_per_clip + token
+ *   - GEMM inputs are bf16, accumulation is fp32 (tcgen05.mma kind::f16 into TMEM)
+ *   - the denoise-step index t is read by the kernels from a device int (`step_ptr`) so that a
+ *     captured CUDA graph of one step can be replayed for every t (1000 replays = one chain)
+ */
+#ifndef GD_B200_H
+#define GD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GD_ABI_VERSION 1
+
+enum gd_status {
+    GD_OK = 0,
+    GD_ERR_INVALID = -1, /* bad argument (shape / alignment / null pointer) */
+    GD_ERR_CUDA = -2,    /* a CUDA runtime / driver call failed            */
+    GD_ERR_ARCH = -3     /* device is not sm_100                           */
+};
+
+enum gd_act { GD_ACT_NONE = 0, GD_ACT_RELU2 = 1, GD_ACT_SILU = 2 };
+
+int gd_abi_version(void);
+const char* gd_last_error(void);
+/* Number of kernels launched by this library since load (bench.py's `gpu_launches`). */
+uint64_t gd_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * gd_linear_bf16:  out = act(A · Wᵀ + bias + rowbias[(row % period) + offset]) + residual
+ *
+ * Replaces every nn.Linear on the path: Q/K/V `models/modules/transformer.py:51,57`, attention
+ * output `transformer.py:73,118`, FeedForward `transformer.py:146-154` (act = GD_ACT_RELU2 is
+ * SquaredReLU `transformer.py:8-16`), emb_x/emb_mem `models/nn.py:189-190,393-394` with the
+ * PositionalEncoding add `transformer.py:176-180` folded in as `rowbias`, blend_layer
+ * `models/model.py:79,105`, the timestep MLP `nn.py:41-46` (GD_ACT_SILU) and the residual adds
+ * `nn.py:99,103,110,118,123,162,167,172`.
+ *
+ *   A        bf16 [M, K], row stride lda (elements, multiple of 8)
+ *   W        bf16 [N, K], row stride ldw  — nn.Linear.weight layout, K-major
+ *   K % 64 == 0, N % 64 == 0 (pad d_pose 123/126 -> 128 on the host)
+ *   bias     fp32 [N] or NULL
+ *   rowbias  fp32 [*, N] or NULL; row r adds rowbias[((r % rowbias_period) + rowbias_offset) * N + col]
+ *   residual fp32 [M, N] row stride ldr, or NULL (may alias out_f32)
+ *   out_f32  fp32 [M, N] row stride ldo_f32, or NULL
+ *   out_bf16 bf16 [M, N] row stride ldo_bf16, or NULL   (at least one output required)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gd_linear_desc {
+    const void* A;
+    const void* W;
+    int32_t M, N, K;
+    int32_t lda, ldw;
+    const float* bias;
+    const float* rowbias;
+    int32_t rowbias_period;
+    int32_t rowbias_offset;
+    const float* residual;
+    int32_t ldr;
+    int32_t act;
+    float* out_f32;
+    int32_t ldo_f32;
+    void* out_bf16;
+    int32_t ldo_bf16;
+} gd_linear_desc;
+
+int gd_linear_bf16(const gd_linear_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * DDPM ancestral update  (models/modules/gaussian_diffusion.py:287-292 _predict_xstart_from_eps,
+ * :207-232 q_posterior_mean_variance, :300-329 p_sample, optional in-paint blend
+ * models/generator.py:255-281), for the step t = *step_ptr:
+ *
+ *   x0   = A[t]*x - B[t]*eps            A = sqrt_recip_alphas_cumprod, B = sqrt_recipm1_alphas_cumprod
+ *   x0   = (1-f[j])*m[n,j]*seed[n,j,c] + f[j]*m[n,j]*x0 + (1-m[n,j])*x0      (only if inpaint_seed)
+ *   mean = C1[t]*x0 + C2[t]*x           posterior_mean_coef1/2
+ *   x'   = mean + (t != 0) * sigma[t] * noise[t]     sigma = exp(0.5*posterior_log_variance_clipped)
+ *
+ * Every product/sum is rounded separately in fp32 (no FMA contraction), which is the order the
+ * reference's elementwise torch ops use.  x / noise / eps_out are (N, C, T) with T contiguous
+ * (the reference's boundary layout, models/model.py:12-15).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gd_ddpm_desc {
+    float* x;                 /* (N, C, T) fp32, updated in place                          */
+    const float* noise_tape;  /* (n_steps, N, C, T) fp32 indexed by t; may be NULL (=0)     */
+    const float* coef_A;      /* [n_steps] each, fp32                                       */
+    const float* coef_B;
+    const float* coef_C1;
+    const float* coef_C2;
+    const float* sigma;
+    const int32_t* step_ptr;  /* device int: current t                                      */
+    int32_t n_clips, C, T;
+    float* eps_out;           /* optional (N, C, T): predicted eps (parity harness)         */
+    float* x0_out;            /* optional (N, C, T): pred_x_start after in-painting         */
+    void* xa_bf16;            /* optional bf16 [N*T, ld_xa]: x' transposed to token rows    */
+    int32_t ld_xa;            /*   (next step's emb_x GEMM operand; cols >= C written as 0) */
+    const float* inpaint_seed;   /* optional (N, T, C) fp32                                 */
+    const float* inpaint_mask;   /* (N, T) fp32, required with inpaint_seed                 */
+    const float* inpaint_factor; /* [T] fp32 trans_factor ramp, required with inpaint_seed  */
+    float clip_x0;            /* > 0: clamp x0 to [-clip, clip]; 0 = off (reference has none) */
+} gd_ddpm_desc;
+
+/* Standalone update from an eps tensor laid out (N, C, T). */
+int gd_ddpm_update(const gd_ddpm_desc* u, const float* eps, void* stream);
+
+/* Final projection (out_layers Linear, models/nn.py:211-214,423-426) with the update above fused
+ * into the GEMM epilogue: eps never round-trips through HBM.  d->N must be 128 >= u->C, the
+ * outputs/residual/rowbias of `d` are ignored, d->M == n_clips*T. */
+int gd_linear_ddpm(const gd_linear_desc* d, const gd_ddpm_desc* u, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * gd_layernorm: nn.LayerNorm([D]) eps 1e-5 (models/nn.py:70-84,141-147,212,424),
+ * fp32 rows in, bf16 rows out (the following GEMM's A operand).  D in {256, 512}.
+ * ------------------------------------------------------------------------------------------ */
+int gd_layernorm(const float* x, int32_t ldx, const float* gamma, const float* beta, void* out_bf16, int32_t ldo,
+                 int32_t M, int32_t D, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * gd_dconv_attention: MultiDConvHeadAttention core (models/modules/transformer.py:88-126):
+ * per (clip, head): Q,K,V = depth-wise conv3 over tokens (SpatialDepthWiseConv :19-44, zero "same"
+ * padding, taps shared by all heads) of the already-projected rows, S = softmax_keys(QKᵀ·scale),
+ * O = S·V.  The token sequence of a clip is the concatenation of up to two row segments
+ * (tedexp joint attention over [x ; memory], models/nn.py:105-113); the conv runs across the seam.
+ *   q/k/v[s]   bf16, row (clip*rows[s] + i) at ptr + row*ld, head h at columns [h*d_k, (h+1)*d_k)
+ *   out[s]     bf16, same row structure as q
+ *   conv_*     fp32 [d_k, 3] taps and [d_k] bias per projection
+ * d_k in {32, 64}; total keys per clip <= 160.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gd_attn_desc {
+    const void* q[2];
+    int32_t q_rows[2];
+    int32_t q_ld[2];
+    const void* k[2];
+    const void* v[2];
+    int32_t kv_rows[2];
+    int32_t kv_ld[2];
+    void* out[2];
+    int32_t out_ld[2];
+    const float* conv_wq;
+    const float* conv_bq;
+    const float* conv_wk;
+    const float* conv_bk;
+    const float* conv_wv;
+    const float* conv_bv;
+    int32_t n_clips, heads, d_k;
+    float scale;
+} gd_attn_desc;
+
+int gd_dconv_attention(const gd_attn_desc* d, void* stream);
+/* Same, but q/k/v rows are fp32 (the fp32-activation parity path); ld in fp32 elements. */
+int gd_dconv_attention_f32in(const gd_attn_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Step-dependent row scatter.  The only t-dependent conditioning is the timestep token
+ * (models/model.py:50-52,90-92 -> memory row 0).  Its image under the loop-invariant linear maps is
+ * tabulated once per chain as table[t, :]; each step copies row t into `row_index` of every
+ * clip's block:   dst[(clip*rows_per_clip + row_index)*ld + j] = table[t*width + j].
+ * Optionally first restores dst from `init` (tedexp: the memory stream is rewritten by the
+ * layers, so each step starts again from emb_mem(speech)+PE, models/nn.py:433-442).
+ * ------------------------------------------------------------------------------------------ */
+int gd_scatter_step_row_f32(float* dst, const float* init, const float* table, const int32_t* step_ptr,
+                            int32_t n_clips, int32_t rows_per_clip, int32_t row_index, int32_t width, int32_t ld,
+                            void* stream);
+int gd_scatter_step_row_bf16(void* dst, const void* table, const int32_t* step_ptr, int32_t n_clips,
+                             int32_t rows_per_clip, int32_t row_index, int32_t width, int32_t ld, void* stream);
+
+/* (N, C, T) fp32 -> bf16 token rows [N*T, ld] (cols >= C zeroed): builds the first emb_x operand from x_T. */
+int gd_pack_pose_rows(const float* x, void* xa_bf16, int32_t n_clips, int32_t C, int32_t T, int32_t ld, void* stream);
+
+/* fp32 -> bf16 row conversion (weights / conditioning repack): dst[r*ldd + c] = src[r*lds + c], c < cols;
+ * columns [cols, cols_padded) are zero-filled. */
+int gd_cast_rows_bf16(const float* src, int32_t lds, void* dst, int32_t ldd, int32_t rows, int32_t cols,
+                      int32_t cols_padded, void* stream);
+
+/* *step_ptr += delta (one thread) — closes a denoise step inside a captured graph. */
+int gd_step_add(int32_t* step_ptr, int32_t delta, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GD_B200_H */

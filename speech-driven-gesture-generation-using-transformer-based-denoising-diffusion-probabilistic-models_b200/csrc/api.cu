@@ -1,0 +1,69 @@
+// C-ABI plumbing: error slot, device checks, launch counter, descriptor validation.
+#include "host_util.h"
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+namespace gd {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+PFN_encodeTiled get_encode_tiled() {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    return reinterpret_cast<PFN_encodeTiled>(fn);
+}
+
+int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+int check_device() {
+    static int ok = -1;
+    if (ok < 0) {
+        int dev = 0, major = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+            return set_error(GD_ERR_CUDA, "no CUDA device available");
+        ok = (major == 10) ? 1 : 0;
+    }
+    if (!ok) return set_error(GD_ERR_ARCH, "these kernels are built for sm_100a (B200) only");
+    return GD_OK;
+}
+
+int validate_ddpm(const gd_ddpm_desc* u) {
+    if (!u) return set_error(GD_ERR_INVALID, "ddpm: null descriptor");
+    if (!u->x || !u->coef_A || !u->coef_B || !u->coef_C1 || !u->coef_C2 || !u->sigma || !u->step_ptr)
+        return set_error(GD_ERR_INVALID, "ddpm: x / coefficient tables / step_ptr must be non-null");
+    if (u->n_clips <= 0 || u->C <= 0 || u->T <= 0) return set_error(GD_ERR_INVALID, "ddpm: bad shape");
+    if (u->inpaint_seed && (!u->inpaint_mask || !u->inpaint_factor))
+        return set_error(GD_ERR_INVALID, "ddpm: inpaint_seed needs inpaint_mask and inpaint_factor");
+    return GD_OK;
+}
+
+}  // namespace gd
+
+extern "C" int gd_abi_version(void) { return GD_ABI_VERSION; }
+extern "C" const char* gd_last_error(void) { return gd::g_err; }
+extern "C" uint64_t gd_launch_count(void) { return gd::g_launches.load(std::memory_order_relaxed); }

@@ -1,0 +1,267 @@
+// HBM-bound row kernels of the sampling chain: LayerNorm (fp32 -> bf16 GEMM operand), the
+// standalone DDPM update, the per-step timestep-row scatter and the layout/cast helpers.
+// All of them are one-pass, 16-byte vectorised and coalesced along the contiguous axis.
+#include "common.cuh"
+#include "ddpm_math.cuh"
+#include "host_util.h"
+
+namespace gd {
+
+// ------------------------------------------------------------------------------- LayerNorm
+// One warp per row, the whole row lives in registers (D/32 floats per lane): one HBM read,
+// one bf16 write, two shuffle reductions (mean, then centred second moment like ATen's
+// two-pass/Welford result — not E[x^2]-E[x]^2, which loses bits when |mean| >> std).
+template <int D>
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __restrict__ x, int ldx,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta,
+                                                             __nv_bfloat16* __restrict__ out, int ldo, int M,
+                                                             float eps) {
+    constexpr int V = D / 128;  // float4 chunks per lane
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int lane = threadIdx.x & 31;
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ldx);
+    float4 v[V];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        v[i] = xr[i * 32 + lane];
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+    uint2* orow = reinterpret_cast<uint2*>(out + (size_t)row * ldo);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const float4 g = __ldg(g4 + i * 32 + lane), b = __ldg(b4 + i * 32 + lane);
+        uint2 w;
+        w.x = pack_bf16x2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+        w.y = pack_bf16x2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+        orow[i * 32 + lane] = w;
+    }
+}
+
+// ------------------------------------------------------------------------------- DDPM update
+// Standalone form (eps already in HBM, (N,C,T)).  One thread per (clip, channel<ld_xa, frame);
+// frame is the fastest index so x/noise/eps accesses are coalesced.
+__global__ void __launch_bounds__(256) ddpm_update_kernel(const gd_ddpm_desc u, const float* __restrict__ eps,
+                                                          int c_span) {
+    const int t = *u.step_ptr;
+    const DdpmStepCoefs cf = ddpm_load_coefs(u, t);
+    const size_t total = (size_t)u.n_clips * c_span * u.T;
+    const size_t tape_base = (size_t)t * u.n_clips * u.C * u.T;
+    const bool inpaint = u.inpaint_seed != nullptr;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int frame = (int)(i % u.T);
+        const int c = (int)((i / u.T) % c_span);
+        const int clip = (int)(i / ((size_t)u.T * c_span));
+        float xnext = 0.f;
+        if (c < u.C) {
+            const size_t idx = ((size_t)clip * u.C + c) * u.T + frame;
+            float m = 0.f, f = 0.f, seed = 0.f;
+            if (inpaint) {
+                m = __ldg(u.inpaint_mask + (size_t)clip * u.T + frame);
+                f = __ldg(u.inpaint_factor + frame);
+                seed = __ldg(u.inpaint_seed + ((size_t)clip * u.T + frame) * u.C + c);
+            }
+            const float z = u.noise_tape ? __ldg(u.noise_tape + tape_base + idx) : 0.f;
+            const float e = eps[idx];
+            float x0;
+            xnext = ddpm_update_elem(cf, u.x[idx], e, z, inpaint, seed, m, f, u.clip_x0, &x0);
+            u.x[idx] = xnext;
+            if (u.eps_out) u.eps_out[idx] = e;
+            if (u.x0_out) u.x0_out[idx] = x0;
+        }
+        if (u.xa_bf16)
+            reinterpret_cast<__nv_bfloat16*>(u.xa_bf16)[((size_t)clip * u.T + frame) * u.ld_xa + c] =
+                __float2bfloat16_rn(xnext);
+    }
+}
+
+// ------------------------------------------------------------------------------- step-row scatter
+__global__ void __launch_bounds__(256) scatter_row_f32_kernel(float* __restrict__ dst, const float* __restrict__ init,
+                                                              const float* __restrict__ table,
+                                                              const int* __restrict__ step_ptr, int n_clips,
+                                                              int rows_per_clip, int row_index, int width, int ld) {
+    const int t = *step_ptr;
+    const int w4 = width >> 2;
+    const float4* trow = reinterpret_cast<const float4*>(table + (size_t)t * width);
+    if (init) {
+        const size_t total = (size_t)n_clips * rows_per_clip * w4;
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+            const int j = (int)(i % w4);
+            const size_t row = i / w4;
+            const bool is_t = (int)(row % rows_per_clip) == row_index;
+            const float4 val = is_t ? __ldg(trow + j) : reinterpret_cast<const float4*>(init + row * ld)[j];
+            reinterpret_cast<float4*>(dst + row * ld)[j] = val;
+        }
+    } else {
+        const size_t total = (size_t)n_clips * w4;
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+            const int j = (int)(i % w4);
+            const size_t row = (i / w4) * rows_per_clip + row_index;
+            reinterpret_cast<float4*>(dst + row * ld)[j] = __ldg(trow + j);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) scatter_row_bf16_kernel(__nv_bfloat16* __restrict__ dst,
+                                                               const __nv_bfloat16* __restrict__ table,
+                                                               const int* __restrict__ step_ptr, int n_clips,
+                                                               int rows_per_clip, int row_index, int width, int ld) {
+    const int t = *step_ptr;
+    const int w8 = width >> 3;
+    const uint4* trow = reinterpret_cast<const uint4*>(table + (size_t)t * width);
+    const size_t total = (size_t)n_clips * w8;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(i % w8);
+        const size_t row = (i / w8) * rows_per_clip + row_index;
+        reinterpret_cast<uint4*>(dst + row * ld)[j] = __ldg(trow + j);
+    }
+}
+
+// ------------------------------------------------------------------------------- layout helpers
+__global__ void __launch_bounds__(256) pack_pose_rows_kernel(const float* __restrict__ x,
+                                                             __nv_bfloat16* __restrict__ xa, int n_clips, int C,
+                                                             int T, int ld) {
+    const size_t total = (size_t)n_clips * T * ld;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % ld);
+        const size_t row = i / ld;
+        const int frame = (int)(row % T);
+        const size_t clip = row / T;
+        xa[i] = __float2bfloat16_rn(c < C ? x[(clip * C + c) * T + frame] : 0.f);
+    }
+}
+
+__global__ void __launch_bounds__(256) cast_rows_bf16_kernel(const float* __restrict__ src, int lds,
+                                                             __nv_bfloat16* __restrict__ dst, int ldd, int rows,
+                                                             int cols, int cols_padded) {
+    const size_t total = (size_t)rows * cols_padded;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cols_padded);
+        const size_t r = i / cols_padded;
+        dst[r * ldd + c] = __float2bfloat16_rn(c < cols ? src[r * lds + c] : 0.f);
+    }
+}
+
+__global__ void step_add_kernel(int* step_ptr, int delta) { *step_ptr += delta; }
+
+static inline int grid_for(size_t total, int block) {
+    size_t g = (total + block - 1) / block;
+    const size_t cap = (size_t)sm_count() * 16;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace gd
+
+using namespace gd;
+
+extern "C" int gd_layernorm(const float* x, int32_t ldx, const float* gamma, const float* beta, void* out_bf16,
+                            int32_t ldo, int32_t M, int32_t D, float eps, void* stream) {
+    if (!x || !gamma || !beta || !out_bf16) return set_error(GD_ERR_INVALID, "gd_layernorm: null pointer");
+    if (M <= 0) return set_error(GD_ERR_INVALID, "gd_layernorm: M <= 0");
+    if (ldx % 4 || ldo % 4 || ldx < D || ldo < D) return set_error(GD_ERR_INVALID, "gd_layernorm: bad row stride");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int wpb = 8, grid = (M + wpb - 1) / wpb;
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+    if (D == 256)
+        layernorm_rows_kernel<256><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, o, ldo, M, eps);
+    else if (D == 512)
+        layernorm_rows_kernel<512><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, o, ldo, M, eps);
+    else if (D == 128)
+        layernorm_rows_kernel<128><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, o, ldo, M, eps);
+    else if (D == 1024)
+        layernorm_rows_kernel<1024><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, o, ldo, M, eps);
+    else
+        return set_error(GD_ERR_INVALID, "gd_layernorm: D=%d unsupported (128/256/512/1024)", D);
+    count_launch();
+    GD_CUDA_CHECK(cudaGetLastError());
+    return GD_OK;
+}
+
+extern "C" int gd_ddpm_update(const gd_ddpm_desc* u, const float* eps, void* stream) {
+    int rc = validate_ddpm(u);
+    if (rc) return rc;
+    if (!eps) return set_error(GD_ERR_INVALID, "gd_ddpm_update: eps is null");
+    int c_span = u->C;
+    if (u->xa_bf16) {
+        if (u->ld_xa < u->C) return set_error(GD_ERR_INVALID, "gd_ddpm_update: ld_xa < C");
+        c_span = u->ld_xa;
+    }
+    const size_t total = (size_t)u->n_clips * c_span * u->T;
+    ddpm_update_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*u, eps, c_span);
+    count_launch();
+    GD_CUDA_CHECK(cudaGetLastError());
+    return GD_OK;
+}
+
+extern "C" int gd_scatter_step_row_f32(float* dst, const float* init, const float* table, const int32_t* step_ptr,
+                                       int32_t n_clips, int32_t rows_per_clip, int32_t row_index, int32_t width,
+                                       int32_t ld, void* stream) {
+    if (!dst || !table || !step_ptr) return set_error(GD_ERR_INVALID, "gd_scatter_step_row_f32: null pointer");
+    if (width % 4 || ld % 4 || ld < width || row_index < 0 || row_index >= rows_per_clip || n_clips <= 0)
+        return set_error(GD_ERR_INVALID, "gd_scatter_step_row_f32: bad shape");
+    const size_t total = init ? (size_t)n_clips * rows_per_clip * (width / 4) : (size_t)n_clips * (width / 4);
+    scatter_row_f32_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        dst, init, table, step_ptr, n_clips, rows_per_clip, row_index, width, ld);
+    count_launch();
+    GD_CUDA_CHECK(cudaGetLastError());
+    return GD_OK;
+}
+
+extern "C" int gd_scatter_step_row_bf16(void* dst, const void* table, const int32_t* step_ptr, int32_t n_clips,
+                                        int32_t rows_per_clip, int32_t row_index, int32_t width, int32_t ld,
+                                        void* stream) {
+    if (!dst || !table || !step_ptr) return set_error(GD_ERR_INVALID, "gd_scatter_step_row_bf16: null pointer");
+    if (width % 8 || ld % 8 || ld < width || row_index < 0 || row_index >= rows_per_clip || n_clips <= 0)
+        return set_error(GD_ERR_INVALID, "gd_scatter_step_row_bf16: bad shape");
+    const size_t total = (size_t)n_clips * (width / 8);
+    scatter_row_bf16_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<__nv_bfloat16*>(dst), reinterpret_cast<const __nv_bfloat16*>(table), step_ptr, n_clips,
+        rows_per_clip, row_index, width, ld);
+    count_launch();
+    GD_CUDA_CHECK(cudaGetLastError());
+    return GD_OK;
+}
+
+extern "C" int gd_pack_pose_rows(const float* x, void* xa_bf16, int32_t n_clips, int32_t C, int32_t T, int32_t ld,
+                                 void* stream) {
+    if (!x || !xa_bf16 || n_clips <= 0 || C <= 0 || T <= 0 || ld < C)
+        return set_error(GD_ERR_INVALID, "gd_pack_pose_rows: bad argument");
+    const size_t total = (size_t)n_clips * T * ld;
+    pack_pose_rows_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        x, reinterpret_cast<__nv_bfloat16*>(xa_bf16), n_clips, C, T, ld);
+    count_launch();
+    GD_CUDA_CHECK(cudaGetLastError());
+    return GD_OK;
+}
+
+extern "C" int gd_cast_rows_bf16(const float* src, int32_t lds, void* dst, int32_t ldd, int32_t rows, int32_t cols,
+                                 int32_t cols_padded, void* stream) {
+    if (!src || !dst || rows <= 0 || cols <= 0 || cols_padded < cols || ldd < cols_padded || lds < cols)
+        return set_error(GD_ERR_INVALID, "gd_cast_rows_bf16: bad argument");
+    const size_t total = (size_t)rows * cols_padded;
+    cast_rows_bf16_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, rows, cols, cols_padded);
+    count_launch();
+    GD_CUDA_CHECK(cudaGetLastError());
+    return GD_OK;
+}
+
+extern "C" int gd_step_add(int32_t* step_ptr, int32_t delta, void* stream) {
+    if (!step_ptr) return set_error(GD_ERR_INVALID, "gd_step_add: null pointer");
+    step_add_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(step_ptr, delta);
+    count_launch();
+    GD_CUDA_CHECK(cudaGetLastError());
+    return GD_OK;
+}

@@ -1,0 +1,403 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:  D[M,N] = A[M,K] · W[N,K]ᵀ  (+ fused epilogue)
+//
+//   warp 0      TMA producer   (cp.async.bulk.tensor 2-D, SWIZZLE_128B tiles, mbarrier ring)
+//   warp 1      MMA issuer     (one thread: tcgen05.mma cta_group::1 kind::f16, 128 x BN x 16)
+//   warp 2      TMEM allocator (512 columns = two BN-wide fp32 accumulator stages for BN <= 256)
+//   warps 4..7  epilogue       (tcgen05.ld 32x32b -> registers -> bias/PE/activation/residual -> HBM)
+//
+// The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile
+// i+1; K is short on this workload (128..2048), so that overlap is where the time is.
+// MODE_DDPM turns the epilogue of the final projection into the DDPM ancestral update
+// (gd_b200.h: gd_linear_ddpm): eps stays in registers.
+#include "common.cuh"
+#include "ddpm_math.cuh"
+#include "host_util.h"
+
+namespace gd {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+constexpr int MODE_STORE = 0;
+constexpr int MODE_DDPM = 1;
+
+struct GemmParams {
+    int M, N, K;
+    const float* bias;
+    const float* rowbias;
+    int rowbias_period, rowbias_offset;
+    const float* residual;
+    int ldr;
+    int act;
+    float* out_f32;
+    int ldo_f32;
+    __nv_bfloat16* out_bf16;
+    int ldo_bf16;
+    gd_ddpm_desc ddpm;
+};
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+    static constexpr int B_BYTES = BN * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == GD_ACT_RELU2) {
+        float r = fmaxf(v, 0.0f);
+        return r * r;
+    }
+    if (act == GD_ACT_SILU) return v / (1.0f + __expf(-v));
+    return v;
+}
+
+// Epilogue for one thread = one output row, 32 consecutive columns starting at col0.
+__device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, int row, int col0, uint32_t (&v)[32]) {
+    float r[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]);
+    if (p.bias) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 b = __ldg(b4 + j);
+            r[4 * j + 0] += b.x;
+            r[4 * j + 1] += b.y;
+            r[4 * j + 2] += b.z;
+            r[4 * j + 3] += b.w;
+        }
+    }
+    if (p.rowbias) {
+        int pos = (row % p.rowbias_period) + p.rowbias_offset;
+        const float4* b4 = reinterpret_cast<const float4*>(p.rowbias + (size_t)pos * p.N + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 b = __ldg(b4 + j);
+            r[4 * j + 0] += b.x;
+            r[4 * j + 1] += b.y;
+            r[4 * j + 2] += b.z;
+            r[4 * j + 3] += b.w;
+        }
+    }
+    if (p.act != GD_ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = apply_act(r[j], p.act);
+    }
+    if (p.residual) {
+        const float4* q4 = reinterpret_cast<const float4*>(p.residual + (size_t)row * p.ldr + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 q = q4[j];
+            r[4 * j + 0] += q.x;
+            r[4 * j + 1] += q.y;
+            r[4 * j + 2] += q.z;
+            r[4 * j + 3] += q.w;
+        }
+    }
+    if (p.out_f32) {
+        float4* o4 = reinterpret_cast<float4*>(p.out_f32 + (size_t)row * p.ldo_f32 + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o4[j] = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+    }
+    if (p.out_bf16) {
+        uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + (size_t)row * p.ldo_bf16 + col0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint4 w;
+            w.x = pack_bf16x2(r[8 * j + 0], r[8 * j + 1]);
+            w.y = pack_bf16x2(r[8 * j + 2], r[8 * j + 3]);
+            w.z = pack_bf16x2(r[8 * j + 4], r[8 * j + 5]);
+            w.w = pack_bf16x2(r[8 * j + 6], r[8 * j + 7]);
+            o4[j] = w;
+        }
+    }
+}
+
+// DDPM epilogue: row = clip*T + frame, columns = pose channels.  Lanes of a warp hold consecutive
+// frames, so for a fixed channel the (N,C,T) accesses of a warp are contiguous.
+__device__ __forceinline__ void epilogue_ddpm_chunk(const GemmParams& p, const DdpmStepCoefs& cf, int t, int row,
+                                                    int col0, uint32_t (&v)[32]) {
+    const gd_ddpm_desc& u = p.ddpm;
+    const int clip = row / u.T;
+    const int frame = row - clip * u.T;
+    const size_t clip_base = (size_t)clip * u.C * u.T + frame;
+    const size_t tape_base = (size_t)t * u.n_clips * u.C * u.T;
+    const bool inpaint = u.inpaint_seed != nullptr;
+    float m = 0.f, f = 0.f;
+    if (inpaint) {
+        m = __ldg(u.inpaint_mask + (size_t)clip * u.T + frame);
+        f = __ldg(u.inpaint_factor + frame);
+    }
+    float xn[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int c = col0 + j;
+        xn[j] = 0.0f;
+        if (c < u.C) {
+            const size_t idx = clip_base + (size_t)c * u.T;
+            const float eps = __uint_as_float(v[j]) + __ldg(p.bias + c);
+            const float x = u.x[idx];
+            const float z = u.noise_tape ? __ldg(u.noise_tape + tape_base + idx) : 0.0f;
+            const float seed = inpaint ? __ldg(u.inpaint_seed + ((size_t)clip * u.T + frame) * u.C + c) : 0.0f;
+            float x0;
+            const float xnext = ddpm_update_elem(cf, x, eps, z, inpaint, seed, m, f, u.clip_x0, &x0);
+            u.x[idx] = xnext;
+            if (u.eps_out) u.eps_out[idx] = eps;
+            if (u.x0_out) u.x0_out[idx] = x0;
+            xn[j] = xnext;
+        }
+    }
+    if (u.xa_bf16) {
+        uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(u.xa_bf16) + (size_t)row * u.ld_xa + col0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint4 w;
+            w.x = pack_bf16x2(xn[8 * j + 0], xn[8 * j + 1]);
+            w.y = pack_bf16x2(xn[8 * j + 2], xn[8 * j + 3]);
+            w.z = pack_bf16x2(xn[8 * j + 4], xn[8 * j + 5]);
+            w.w = pack_bf16x2(xn[8 * j + 6], xn[8 * j + 7]);
+            o4[j] = w;
+        }
+    }
+}
+
+template <int BN, int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmParams p) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = bars;                    // [STAGES]  TMA -> MMA
+    uint64_t* empty_bar = bars + STAGES;          // [STAGES]  MMA -> TMA
+    uint64_t* acc_full_bar = bars + 2 * STAGES;   // [2]       MMA -> epilogue
+    uint64_t* acc_empty_bar = acc_full_bar + 2;   // [2]       epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+    const int n_tiles = p.N / BN;
+    const int num_tiles = m_tiles * n_tiles;
+    const int k_blocks = p.K / BLOCK_K;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&tmap_a);
+        prefetch_tensormap(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&acc_full_bar[s], 1);
+            mbar_init(&acc_empty_bar[s], 4);  // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles) * BLOCK_M;
+                const int n0 = (tile % n_tiles) * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K, m0);
+                    tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmap_b, &full_bar[stage], kb * BLOCK_K, n0);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&acc_empty_bar[acc], acc_phase ^ 1);
+                tc_fence_after_sync();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after_sync();
+                    const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::A_BYTES));
+                    const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::B_BYTES));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // +32 B per UMMA_K step inside the 128-B swizzle row: start-address field += 2
+                        umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&acc_full_bar[acc]);  // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        const int ew = warp - 4;  // TMEM lanes [32*ew, 32*ew+32)
+        int t = 0;
+        DdpmStepCoefs cf;
+        if (MODE == MODE_DDPM) {
+            t = *p.ddpm.step_ptr;
+            cf = ddpm_load_coefs(p.ddpm, t);
+        }
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int m0 = (tile / n_tiles) * BLOCK_M;
+            const int n0 = (tile % n_tiles) * BN;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&acc_full_bar[acc], acc_phase);
+            tc_fence_after_sync();
+            const int row = m0 + ew * 32 + lane;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(taddr + c * 32, v);
+                tmem_ld_wait();
+                if (row < p.M) {
+                    if (MODE == MODE_DDPM)
+                        epilogue_ddpm_chunk(p, cf, t, row, n0 + c * 32, v);
+                    else
+                        epilogue_store_chunk(p, row, n0 + c * 32, v);
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty_bar[acc]);
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------ host
+static int make_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                             uint32_t box_rows) {
+    static PFN_encodeTiled encode = get_encode_tiled();
+    if (!encode) return set_error(GD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld_elems * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(GD_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return GD_OK;
+}
+
+template <int BN, int MODE>
+static int launch_gemm(const GemmParams& p, const void* A, int lda, const void* W, int ldw, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    CUtensorMap ta, tb;
+    int rc = make_tmap_2d_bf16(&ta, A, p.M, p.K, lda, BLOCK_M);
+    if (rc) return rc;
+    rc = make_tmap_2d_bf16(&tb, W, p.N, p.K, ldw, BN);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GD_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+    const int tiles = m_tiles * (p.N / BN);
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    gemm_bf16_tn_kernel<BN, MODE><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+    count_launch();
+    GD_CUDA_CHECK(cudaGetLastError());
+    return GD_OK;
+}
+
+static int validate_linear(const gd_linear_desc* d) {
+    if (!d || !d->A || !d->W) return set_error(GD_ERR_INVALID, "gd_linear: null descriptor/operand");
+    if (d->M <= 0 || d->N <= 0 || d->K <= 0) return set_error(GD_ERR_INVALID, "gd_linear: non-positive shape");
+    if (d->K % BLOCK_K) return set_error(GD_ERR_INVALID, "gd_linear: K=%d must be a multiple of 64", d->K);
+    if (d->N % 64) return set_error(GD_ERR_INVALID, "gd_linear: N=%d must be a multiple of 64", d->N);
+    if (d->lda % 8 || d->ldw % 8 || d->lda < d->K || d->ldw < d->K)
+        return set_error(GD_ERR_INVALID, "gd_linear: lda/ldw must be >= K and multiples of 8");
+    if ((reinterpret_cast<uintptr_t>(d->A) | reinterpret_cast<uintptr_t>(d->W)) & 15)
+        return set_error(GD_ERR_INVALID, "gd_linear: A/W must be 16-byte aligned");
+    return GD_OK;
+}
+
+}  // namespace gd
+
+using namespace gd;
+
+extern "C" int gd_linear_bf16(const gd_linear_desc* d, void* stream) {
+    int rc = validate_linear(d);
+    if (rc) return rc;
+    if (!d->out_f32 && !d->out_bf16) return set_error(GD_ERR_INVALID, "gd_linear_bf16: no output buffer");
+    if ((d->out_f32 && d->ldo_f32 % 4) || (d->out_bf16 && d->ldo_bf16 % 8) || (d->residual && d->ldr % 4))
+        return set_error(GD_ERR_INVALID, "gd_linear_bf16: output/residual row strides must keep 16-byte alignment");
+    if (d->rowbias && d->rowbias_period <= 0) return set_error(GD_ERR_INVALID, "gd_linear_bf16: rowbias_period <= 0");
+    rc = check_device();
+    if (rc) return rc;
+    GemmParams p{};
+    p.M = d->M, p.N = d->N, p.K = d->K;
+    p.bias = d->bias, p.rowbias = d->rowbias;
+    p.rowbias_period = d->rowbias_period, p.rowbias_offset = d->rowbias_offset;
+    p.residual = d->residual, p.ldr = d->ldr, p.act = d->act;
+    p.out_f32 = d->out_f32, p.ldo_f32 = d->ldo_f32;
+    p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(d->out_bf16), p.ldo_bf16 = d->ldo_bf16;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int m_tiles = (d->M + BLOCK_M - 1) / BLOCK_M;
+    // Widest tile that still gives every SM work; narrow tiles when the problem is small.
+    if (d->N % 256 == 0 && m_tiles * (d->N / 256) >= sm_count())
+        return launch_gemm<256, MODE_STORE>(p, d->A, d->lda, d->W, d->ldw, s);
+    if (d->N % 128 == 0 && m_tiles * (d->N / 128) >= sm_count())
+        return launch_gemm<128, MODE_STORE>(p, d->A, d->lda, d->W, d->ldw, s);
+    return launch_gemm<64, MODE_STORE>(p, d->A, d->lda, d->W, d->ldw, s);
+}
+
+extern "C" int gd_linear_ddpm(const gd_linear_desc* d, const gd_ddpm_desc* u, void* stream) {
+    int rc = validate_linear(d);
+    if (rc) return rc;
+    rc = validate_ddpm(u);
+    if (rc) return rc;
+    if (d->N != 128 || u->C > 128) return set_error(GD_ERR_INVALID, "gd_linear_ddpm: N must be 128 (padded d_pose)");
+    if (d->M != u->n_clips * u->T) return set_error(GD_ERR_INVALID, "gd_linear_ddpm: M != n_clips*T");
+    if (!d->bias) return set_error(GD_ERR_INVALID, "gd_linear_ddpm: bias required");
+    if (u->xa_bf16 && (u->ld_xa % 8 || u->ld_xa < 128))
+        return set_error(GD_ERR_INVALID, "gd_linear_ddpm: ld_xa must be >= 128 and a multiple of 8");
+    rc = check_device();
+    if (rc) return rc;
+    GemmParams p{};
+    p.M = d->M, p.N = d->N, p.K = d->K;
+    p.bias = d->bias;
+    p.ddpm = *u;
+    return launch_gemm<128, MODE_DDPM>(p, d->A, d->lda, d->W, d->ldw, reinterpret_cast<cudaStream_t>(stream));
+}

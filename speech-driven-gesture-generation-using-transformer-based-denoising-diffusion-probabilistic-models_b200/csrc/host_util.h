@@ -1,0 +1,28 @@
+// Host-side plumbing shared by the launchers: error slot, device checks, launch counter.
+#pragma once
+#include "../../include/gd_b200.h"
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace gd {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int set_error(int code, const char* fmt, ...);  // returns code
+PFN_encodeTiled get_encode_tiled();             // resolved through cudaGetDriverEntryPoint (no -lcuda link)
+int sm_count();                                 // SMs of the current device (148 on B200)
+int check_device();                             // GD_OK iff current device is compute capability 10.x
+void count_launch();
+int validate_ddpm(const gd_ddpm_desc* u);
+
+#define GD_CUDA_CHECK(expr)                                                                          \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return ::gd::set_error(GD_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                   __FILE__, __LINE__);                                              \
+    } while (0)
+
+}  // namespace gd

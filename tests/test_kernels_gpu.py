@@ -1,0 +1,258 @@
+"""GPU parity of each C-ABI kernel against a plain torch fp32 statement of the same op."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _linear(gd, A, W, bias=None, rowbias=None, period=0, offset=0, residual=None, act=0, want_f32=True, want_bf16=False):
+    M, K = A.shape
+    N = W.shape[0]
+    d = gd.LinearDesc()
+    d.A, d.W, d.M, d.N, d.K, d.lda, d.ldw = A.data_ptr(), W.data_ptr(), M, N, K, A.stride(0), W.stride(0)
+    d.bias = gd.ptr(bias)
+    d.rowbias, d.rowbias_period, d.rowbias_offset = gd.ptr(rowbias), period, offset
+    d.residual, d.ldr = gd.ptr(residual), (residual.stride(0) if residual is not None else 0)
+    d.act = act
+    o32 = torch.empty(M, N, device="cuda", dtype=torch.float32) if want_f32 else None
+    o16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16) if want_bf16 else None
+    d.out_f32, d.ldo_f32 = gd.ptr(o32), N
+    d.out_bf16, d.ldo_bf16 = gd.ptr(o16), N
+    gd.check(gd.load().gd_linear_bf16(C.byref(d), _stream()), "gd_linear_bf16")
+    torch.cuda.synchronize()
+    return o32, o16
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (128, 128, 64), (256, 256, 128), (5120, 256, 256), (1000, 768, 256),
+                                   (8704, 1536, 512), (8704, 512, 2048), (35328, 512, 512), (77, 128, 128),
+                                   (40960, 1024, 256), (20000, 2048, 512)])
+def test_linear_plain(gd, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    o32, _ = _linear(gd, A, W)
+    ref = A.float() @ W.float().t()
+    err = (o32 - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), err
+
+
+def test_linear_epilogue(gd):
+    M, N, K, T = 4000, 256, 128, 40
+    g = torch.Generator(device="cuda").manual_seed(7)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    pe = torch.randn(T + 3, N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    base = A.float() @ W.float().t() + bias
+    rows = torch.arange(M, device="cuda")
+    # bias + PE rowbias + residual, fp32 + bf16 outputs
+    o32, o16 = _linear(gd, A, W, bias=bias, rowbias=pe, period=T, offset=3, residual=res, want_bf16=True)
+    ref = base + pe[(rows % T) + 3] + res
+    assert (o32 - ref).abs().max().item() < 5e-3
+    assert (o16.float() - ref).abs().max().item() < 5e-2
+    # squared ReLU
+    o32, _ = _linear(gd, A, W, bias=bias, act=gd.ACT_RELU2)
+    assert (o32 - torch.relu(base) ** 2).abs().max().item() < 2e-2
+    # SiLU
+    o32, _ = _linear(gd, A, W, bias=bias, act=gd.ACT_SILU)
+    assert (o32 - torch.nn.functional.silu(base)).abs().max().item() < 5e-3
+    # in-place residual (residual aliases the output)
+    d = gd.LinearDesc()
+    x = res.clone()
+    d.A, d.W, d.M, d.N, d.K, d.lda, d.ldw = A.data_ptr(), W.data_ptr(), M, N, K, K, K
+    d.bias, d.residual, d.ldr, d.out_f32, d.ldo_f32 = bias.data_ptr(), x.data_ptr(), N, x.data_ptr(), N
+    gd.check(gd.load().gd_linear_bf16(C.byref(d), _stream()))
+    torch.cuda.synchronize()
+    assert (x - (base + res)).abs().max().item() < 5e-3
+
+
+def test_linear_rejects_bad_shapes(gd):
+    A = torch.zeros(128, 72, device="cuda", dtype=torch.bfloat16)
+    W = torch.zeros(64, 72, device="cuda", dtype=torch.bfloat16)
+    d = gd.LinearDesc()
+    d.A, d.W, d.M, d.N, d.K, d.lda, d.ldw = A.data_ptr(), W.data_ptr(), 128, 64, 72, 72, 72
+    assert gd.load().gd_linear_bf16(C.byref(d), _stream()) == -1
+    assert b"multiple of 64" in gd.load().gd_last_error()
+
+
+@pytest.mark.parametrize("D,M", [(256, 5120), (512, 35328), (256, 3)])
+def test_layernorm(gd, D, M):
+    g = torch.Generator(device="cuda").manual_seed(D + M)
+    x = torch.randn(M, D, device="cuda", generator=g) * 3 + 1.5
+    gamma = torch.randn(D, device="cuda", generator=g)
+    beta = torch.randn(D, device="cuda", generator=g)
+    out = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+    gd.check(gd.load().gd_layernorm(x.data_ptr(), D, gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), D, M, D, 1e-5,
+                                    _stream()))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x, (D,), gamma, beta, 1e-5)
+    assert torch.equal(out, ref.bfloat16()) or (out.float() - ref).abs().max().item() < 4e-2
+    # at most 1 bf16 ulp away from the rounded fp32 result
+    assert ((out.float() - ref).abs() <= ref.abs() * 2 ** -7 + 1e-6).all()
+
+
+def _ref_dconv(u, w, b):
+    # u: (N, L, H, dk) -> depth-wise conv3 over L with zero same-padding (transformer.py:19-44)
+    N, L, H, dk = u.shape
+    z = u.permute(0, 2, 3, 1).reshape(N * H, dk, L)
+    z = torch.nn.functional.conv1d(z, w.view(dk, 1, 3), b, padding=1, groups=dk)
+    return z.view(N, H, dk, L).permute(0, 3, 1, 2)
+
+
+def _ref_attention(q, k, v, taps, scale):
+    q = _ref_dconv(q, taps[0], taps[1])
+    k = _ref_dconv(k, taps[2], taps[3])
+    v = _ref_dconv(v, taps[4], taps[5])
+    s = torch.einsum("nihd,njhd->nhij", q, k) * scale
+    p = torch.softmax(s, dim=-1)
+    return torch.einsum("nhij,njhd->nihd", p, v)
+
+
+@pytest.mark.parametrize("dk,rows_q,rows_kv,f32", [(32, (40, 0), (40, 0), False), (32, (40, 0), (32, 0), False),
+                                                    (64, (34, 104), (34, 104), False), (64, (104, 0), (104, 0), True),
+                                                    (32, (160, 0), (127, 0), False)])
+def test_dconv_attention(gd, dk, rows_q, rows_kv, f32):
+    N, H = 5, 8
+    d_model = H * dk
+    g = torch.Generator(device="cuda").manual_seed(dk + sum(rows_q))
+    dt = torch.float32 if f32 else torch.bfloat16
+    self_attn = rows_q == rows_kv
+    segs_q = [torch.randn(N * r, 3 * d_model, device="cuda", generator=g).to(dt) if r else None for r in rows_q]
+    segs_kv = segs_q if self_attn else [torch.randn(N * r, 3 * d_model, device="cuda", generator=g).to(dt) if r else None for r in rows_kv]
+    taps = [torch.randn(dk, 3, device="cuda", generator=g) * 0.5 if i % 2 == 0 else torch.randn(dk, device="cuda", generator=g) * 0.1 for i in range(6)]
+    outs = [torch.zeros(N * r, d_model, device="cuda", dtype=torch.bfloat16) if r else None for r in rows_q]
+    a = gd.AttnDesc()
+    es = 4 if f32 else 2
+    for s in range(2):
+        if segs_q[s] is not None:
+            a.q[s], a.q_rows[s], a.q_ld[s] = segs_q[s].data_ptr(), rows_q[s], 3 * d_model
+            a.out[s], a.out_ld[s] = outs[s].data_ptr(), d_model
+        if segs_kv[s] is not None:
+            a.k[s] = segs_kv[s].data_ptr() + d_model * es
+            a.v[s] = segs_kv[s].data_ptr() + 2 * d_model * es
+            a.kv_rows[s], a.kv_ld[s] = rows_kv[s], 3 * d_model
+    a.conv_wq, a.conv_bq, a.conv_wk, a.conv_bk, a.conv_wv, a.conv_bv = [t.data_ptr() for t in taps]
+    a.n_clips, a.heads, a.d_k, a.scale = N, H, dk, 1.0 / math.sqrt(dk)
+    fn = gd.load().gd_dconv_attention_f32in if f32 else gd.load().gd_dconv_attention
+    gd.check(fn(C.byref(a), _stream()))
+    torch.cuda.synchronize()
+
+    def cat(segs, rows, lo):
+        parts = [sg.float().view(N, r, 3 * d_model)[:, :, lo:lo + d_model] for sg, r in zip(segs, rows) if r]
+        return torch.cat(parts, dim=1).reshape(N, -1, H, dk)
+    ref = _ref_attention(cat(segs_q, rows_q, 0), cat(segs_kv, rows_kv, d_model), cat(segs_kv, rows_kv, 2 * d_model),
+                         taps, a.scale).reshape(N, -1, d_model)
+    got = torch.cat([o.view(N, r, d_model) for o, r in zip(outs, rows_q) if r], dim=1).float()
+    assert (got - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item())
+
+
+def _tables(n=1000):
+    g = torch.Generator().manual_seed(3)
+    return [torch.rand(n, generator=g).cuda() + 0.5 for _ in range(5)]
+
+
+@pytest.mark.parametrize("inpaint", [False, True])
+def test_ddpm_update_standalone(gd, inpaint):
+    N, Cc, T = 7, 123, 40
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(N, Cc, T, device="cuda", generator=g)
+    eps = torch.randn(N, Cc, T, device="cuda", generator=g)
+    tape = torch.randn(3, N, Cc, T, device="cuda", generator=g)
+    A, B, C1, C2, sg = _tables(3)
+    for t in (2, 0):
+        step = torch.tensor([t], device="cuda", dtype=torch.int32)
+        xa = torch.full((N * T, 128), 7.0, device="cuda", dtype=torch.bfloat16)
+        x0o = torch.empty_like(x)
+        xin = x.clone()
+        u = gd.DdpmDesc()
+        u.x, u.noise_tape = xin.data_ptr(), tape.data_ptr()
+        u.coef_A, u.coef_B, u.coef_C1, u.coef_C2, u.sigma = [v.data_ptr() for v in (A, B, C1, C2, sg)]
+        u.step_ptr, u.n_clips, u.C, u.T = step.data_ptr(), N, Cc, T
+        u.x0_out, u.xa_bf16, u.ld_xa = x0o.data_ptr(), xa.data_ptr(), 128
+        if inpaint:
+            seed = torch.randn(N, T, Cc, device="cuda", generator=g)
+            mask = torch.zeros(N, T, device="cuda")
+            mask[:, :10] = 1
+            f = torch.cat([torch.arange(0.575, 1, (1 - 0.575) / 10), torch.ones(T - 10)]).cuda()
+            u.inpaint_seed, u.inpaint_mask, u.inpaint_factor = seed.data_ptr(), mask.data_ptr(), f.data_ptr()
+        gd.check(gd.load().gd_ddpm_update(C.byref(u), eps.data_ptr(), _stream()))
+        torch.cuda.synchronize()
+        x0 = A[t] * x - B[t] * eps
+        if inpaint:
+            x0t = x0.transpose(1, 2)
+            m3, f3 = mask[:, :, None], f[None, :, None]
+            x0 = ((1 - f3) * m3 * seed + f3 * m3 * x0t + (1 - m3) * x0t).transpose(1, 2)
+        mean = C1[t] * x0 + C2[t] * x
+        ref = mean + (0.0 if t == 0 else 1.0) * sg[t] * tape[t]
+        assert torch.equal(x0o, x0.contiguous())
+        assert torch.equal(xin, ref)  # same rounding order as the torch elementwise chain -> bit exact
+        assert torch.equal(xa[:, :Cc].view(N, T, Cc), ref.transpose(1, 2).bfloat16())
+        assert (xa[:, Cc:] == 0).all()
+
+
+def test_linear_ddpm_fused(gd):
+    N, Cc, T, K = 33, 126, 34, 512
+    M = N * T
+    g = torch.Generator(device="cuda").manual_seed(5)
+    Aop = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = torch.zeros(128, K, device="cuda", dtype=torch.bfloat16)
+    W[:Cc] = (torch.randn(Cc, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.zeros(128, device="cuda")
+    bias[:Cc] = torch.randn(Cc, device="cuda", generator=g)
+    x = torch.randn(N, Cc, T, device="cuda", generator=g)
+    tape = torch.randn(2, N, Cc, T, device="cuda", generator=g)
+    A, B, C1, C2, sg = _tables(2)
+    step = torch.tensor([1], device="cuda", dtype=torch.int32)
+    xin, eps_o = x.clone(), torch.empty_like(x)
+    xa = torch.full((M, 128), 7.0, device="cuda", dtype=torch.bfloat16)
+    d = gd.LinearDesc()
+    d.A, d.W, d.M, d.N, d.K, d.lda, d.ldw, d.bias = Aop.data_ptr(), W.data_ptr(), M, 128, K, K, K, bias.data_ptr()
+    u = gd.DdpmDesc()
+    u.x, u.noise_tape = xin.data_ptr(), tape.data_ptr()
+    u.coef_A, u.coef_B, u.coef_C1, u.coef_C2, u.sigma = [v.data_ptr() for v in (A, B, C1, C2, sg)]
+    u.step_ptr, u.n_clips, u.C, u.T = step.data_ptr(), N, Cc, T
+    u.eps_out, u.xa_bf16, u.ld_xa = eps_o.data_ptr(), xa.data_ptr(), 128
+    gd.check(gd.load().gd_linear_ddpm(C.byref(d), C.byref(u), _stream()))
+    torch.cuda.synchronize()
+    eps_ref = (Aop.float() @ W.float().t() + bias)[:, :Cc].view(N, T, Cc).transpose(1, 2)
+    assert (eps_o - eps_ref).abs().max().item() < 5e-3
+    x0 = A[1] * x - B[1] * eps_o
+    ref = C1[1] * x0 + C2[1] * x + sg[1] * tape[1]
+    assert torch.equal(xin, ref)  # given the kernel's own eps the update is bit exact
+    assert torch.equal(xa[:, :Cc].view(N, T, Cc), ref.transpose(1, 2).bfloat16())
+    assert (xa[:, Cc:] == 0).all()
+
+
+def test_step_row_scatter_and_helpers(gd):
+    lib = gd.load()
+    N, R, Wd = 6, 104, 512
+    table = torch.randn(10, Wd, device="cuda")
+    init = torch.randn(N * R, Wd, device="cuda")
+    dst = torch.zeros_like(init)
+    step = torch.tensor([4], device="cuda", dtype=torch.int32)
+    gd.check(lib.gd_scatter_step_row_f32(dst.data_ptr(), init.data_ptr(), table.data_ptr(), step.data_ptr(), N, R, 0, Wd, Wd, _stream()))
+    ref = init.clone().view(N, R, Wd)
+    ref[:, 0] = table[4]
+    assert torch.equal(dst.view(N, R, Wd), ref)
+    tb = torch.randn(10, Wd, device="cuda").bfloat16()
+    db = torch.zeros(N * 32, Wd, device="cuda", dtype=torch.bfloat16)
+    gd.check(lib.gd_scatter_step_row_bf16(db.data_ptr(), tb.data_ptr(), step.data_ptr(), N, 32, 0, Wd, Wd, _stream()))
+    assert torch.equal(db.view(N, 32, Wd)[:, 0], tb[4].expand(N, Wd)) and (db.view(N, 32, Wd)[:, 1:] == 0).all()
+    gd.check(lib.gd_step_add(step.data_ptr(), -1, _stream()))
+    assert step.item() == 3
+    x = torch.randn(N, 123, 40, device="cuda")
+    xa = torch.empty(N * 40, 128, device="cuda", dtype=torch.bfloat16)
+    gd.check(lib.gd_pack_pose_rows(x.data_ptr(), xa.data_ptr(), N, 123, 40, 128, _stream()))
+    assert torch.equal(xa[:, :123].view(N, 40, 123), x.transpose(1, 2).bfloat16()) and (xa[:, 123:] == 0).all()
+    src = torch.randn(50, 123, device="cuda")
+    dstb = torch.empty(50, 128, device="cuda", dtype=torch.bfloat16)
+    gd.check(lib.gd_cast_rows_bf16(src.data_ptr(), 123, dstb.data_ptr(), 128, 50, 123, 128, _stream()))
+    assert torch.equal(dstb[:, :123], src.bfloat16()) and (dstb[:, 123:] == 0).all()
