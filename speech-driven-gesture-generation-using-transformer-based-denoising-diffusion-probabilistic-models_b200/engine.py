@@ -1,0 +1,480 @@
+"""Host-side driver of the sampling chain: packs weights once, hoists the loop-invariant conditioning, builds the
+per-step launch plan over the C-ABI kernels (include/gd_b200.h) and replays it as a CUDA graph.
+
+Data layout in HBM (per engine, N clips):
+  x        (N, C, T) fp32      the sample, boundary layout of the reference (models/model.py:12-15)
+  xa       [N*T, 128] bf16     x transposed to token rows, d_pose zero-padded to 128 (emb_x GEMM operand)
+  H        [rows, d] fp32      residual stream(s); tedexp: pose rows [0, N*Tx) then memory rows [N*Tx, N*(Tx+Tm))
+  xn/ao    [rows, d] bf16      LayerNorm output / attention output (GEMM operands)
+  qkv      [rows, 3d] bf16     fused Q|K|V projection (fp32 in the `fp32act` precision mode)
+  hid      [rows, 4d] bf16     FFN hidden after squared ReLU
+  tape     (n_steps, N, C, T)  pre-generated Gaussian noise indexed by loop index i
+The step index lives in a device int; every kernel that depends on it reads it there, so ONE captured
+step graph serves all steps and `graph_steps` consecutive steps can be captured into a single graph.
+"""
+import ctypes as C
+import math
+
+import torch as th
+
+from . import _lib as gd
+from .modules import positional_table, step_embedding_table
+
+_POSE_PAD = 128
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+class PackedWeights:
+    """bf16/fp32 repack of a denoiser's parameters for the kernels (done once per weight version)."""
+
+    def __init__(self, model, diffusion, device):
+        self.device = device
+        sd = {k: v.detach().to(device=device, dtype=th.float32) for k, v in model.state_dict().items()
+              if v.dtype.is_floating_point}
+        self.kind = model.pose_decoder.kind
+        self.d = d = model.d_model
+        self.C = model.d_pose
+        self.heads = model.pose_decoder.heads
+        self.n_layers = model.pose_decoder.n_layers
+        bf = lambda w: w.to(th.bfloat16).contiguous()  # noqa: E731
+        f32 = lambda w: w.float().contiguous()  # noqa: E731
+        pd = "pose_decoder."
+        w = sd[pd + "emb_x.weight"]
+        wx = th.zeros(d, _POSE_PAD, device=device)
+        wx[:, :self.C] = w
+        self.embx_w, self.embx_b = bf(wx), f32(sd[pd + "emb_x.bias"])
+        self.embm_w, self.embm_b = bf(sd[pd + "emb_mem.weight"]), f32(sd[pd + "emb_mem.bias"])
+        wo = th.zeros(_POSE_PAD, d, device=device)
+        wo[:self.C] = sd[pd + "out_layers.1.weight"]
+        bo = th.zeros(_POSE_PAD, device=device)
+        bo[:self.C] = sd[pd + "out_layers.1.bias"]
+        self.out_w, self.out_b = bf(wo), f32(bo)
+        self.out_ln = (f32(sd[pd + "out_layers.0.weight"]), f32(sd[pd + "out_layers.0.bias"]))
+
+        def attn(prefix):
+            a = {}
+            names = ("query", "key", "value")
+            a["wqkv"] = bf(th.cat([sd[f"{prefix}.{n}.0.linear.weight"] for n in names], 0))
+            a["bqkv"] = f32(th.cat([sd[f"{prefix}.{n}.0.linear.bias"] for n in names], 0))
+            a["taps"] = [f32(sd[f"{prefix}.{n}.1.conv.{p}"].reshape(-1, 3) if p == "weight" else sd[f"{prefix}.{n}.1.conv.{p}"])
+                         for n in names for p in ("weight", "bias")]  # wq,bq,wk,bk,wv,bv
+            a["wo"], a["bo"] = bf(sd[prefix + ".output.weight"]), f32(sd[prefix + ".output.bias"])
+            return a
+
+        def ffn(prefix):
+            return {"w1": bf(sd[prefix + ".layer1.weight"]), "b1": f32(sd[prefix + ".layer1.bias"]),
+                    "w2": bf(sd[prefix + ".layer2.weight"]), "b2": f32(sd[prefix + ".layer2.bias"])}
+
+        def ln(prefix):
+            return (f32(sd[prefix + ".weight"]), f32(sd[prefix + ".bias"]))
+
+        self.layers = []
+        for l in range(self.n_layers):
+            k = f"{pd}layers.{l}."
+            L = {"ln_sa": ln(k + "norm_self_attn"), "sa": attn(k + "self_attn"), "ln_ca": ln(k + "norm_cross_attn"),
+                 "ca": attn(k + "cross_attn"), "ln_ff": ln(k + "norm_ff"), "ff": ffn(k + "feed_forward")}
+            if self.kind == "cross_attention":
+                L["ln_sam"], L["sam"] = ln(k + "norm_self_attn_mem"), attn(k + "self_attn_mem")
+                if k + "feed_forward_mem.layer1.weight" in sd:
+                    L["ln_ffm"], L["ffm"] = ln(k + "norm_ff_mem"), ffn(k + "feed_forward_mem")
+            self.layers.append(L)
+        if self.kind == "oneway_cross_attention":
+            # all layers' cross-attention K|V projections side by side: one GEMM hoists them per chain
+            self.ca_wkv = bf(th.cat([th.cat([sd[f"{pd}layers.{l}.cross_attn.{n}.0.linear.weight"] for n in ("key", "value")], 0)
+                                     for l in range(self.n_layers)], 0))
+            self.ca_bkv = f32(th.cat([th.cat([sd[f"{pd}layers.{l}.cross_attn.{n}.0.linear.bias"] for n in ("key", "value")], 0)
+                                      for l in range(self.n_layers)], 0))
+        self.has_blend = "blend_layer.weight" in sd
+        if self.has_blend:
+            self.blend_w, self.blend_b = bf(sd["blend_layer.weight"]), f32(sd["blend_layer.bias"])
+        self.tmlp = (bf(sd["diffusion_step_encoder.proj.0.weight"]), f32(sd["diffusion_step_encoder.proj.0.bias"]),
+                     bf(sd["diffusion_step_encoder.proj.2.weight"]), f32(sd["diffusion_step_encoder.proj.2.bias"]))
+        self.pe = positional_table(d, 512).to(device)
+        # sinusoidal embedding of the ORIGINAL timestep of every loop index (respace.py:104-113 remap)
+        tmap = th.tensor(diffusion.timestep_map, dtype=th.long)
+        self.t_embed = step_embedding_table(d, diffusion.original_num_steps)[tmap].to(device).to(th.bfloat16).contiguous()
+        self.n_steps = diffusion.num_timesteps
+
+
+class _Launcher:
+    """Thin typed wrappers over the C-ABI; every call goes to libgd_b200.so on the current torch stream."""
+
+    def __init__(self):
+        self.lib = gd.load()
+        self.keep = []  # tensors that descriptors point into
+
+    @staticmethod
+    def stream():
+        return th.cuda.current_stream().cuda_stream
+
+    def linear(self, A, W, M, N, K, bias=None, rowbias=None, period=0, offset=0, residual=None, act=gd.ACT_NONE,
+               out_f32=None, out_bf16=None, lda=None, ldo32=None, ldo16=None):
+        d = gd.LinearDesc()
+        d.A, d.W, d.M, d.N, d.K = _p(A), _p(W), M, N, K
+        d.lda, d.ldw = (lda or A.stride(0)), W.stride(0)
+        d.bias, d.rowbias, d.rowbias_period, d.rowbias_offset = _p(bias), _p(rowbias), period, offset
+        d.residual, d.ldr = _p(residual), (residual.stride(0) if residual is not None else 0)
+        d.act = act
+        d.out_f32, d.ldo_f32 = _p(out_f32), (ldo32 or (out_f32.stride(0) if out_f32 is not None else 0))
+        d.out_bf16, d.ldo_bf16 = _p(out_bf16), (ldo16 or (out_bf16.stride(0) if out_bf16 is not None else 0))
+        lib = self.lib
+        return lambda: gd.check(lib.gd_linear_bf16(C.byref(d), self.stream()), "gd_linear_bf16")
+
+    def layernorm(self, x, gamma_beta, out, M, D):
+        lib, g, b = self.lib, gamma_beta[0], gamma_beta[1]
+        args = (_p(x), x.stride(0), _p(g), _p(b), _p(out), out.stride(0), M, D, 1e-5)
+        return lambda: gd.check(lib.gd_layernorm(*args, self.stream()), "gd_layernorm")
+
+    def attention(self, n_clips, heads, d_k, q, k, v, out, taps, f32in):
+        """q/k/v/out: lists of up to two (tensor_view, rows_per_clip) segments; views start at the right column."""
+        a = gd.AttnDesc()
+        for s, (t, rows) in enumerate(q):
+            a.q[s], a.q_rows[s], a.q_ld[s] = _p(t), rows, t.stride(0)
+        for s, ((tk, rows), (tv, _)) in enumerate(zip(k, v)):
+            a.k[s], a.v[s], a.kv_rows[s], a.kv_ld[s] = _p(tk), _p(tv), rows, tk.stride(0)
+        for s, (t, _) in enumerate(out):
+            a.out[s], a.out_ld[s] = _p(t), t.stride(0)
+        a.conv_wq, a.conv_bq, a.conv_wk, a.conv_bk, a.conv_wv, a.conv_bv = [_p(t) for t in taps]
+        a.n_clips, a.heads, a.d_k, a.scale = n_clips, heads, d_k, 1.0 / math.sqrt(d_k)
+        fn = self.lib.gd_dconv_attention_f32in if f32in else self.lib.gd_dconv_attention
+        return lambda: gd.check(fn(C.byref(a), self.stream()), "gd_dconv_attention")
+
+
+class SamplingChain:
+    """One (model, diffusion, batch shape, algorithm) sampling context: buffers + plan + captured graph."""
+
+    def __init__(self, model, diffusion, shape, alg, device, precision="bf16", graph_steps=1, use_graph=True):
+        if device.type != "cuda":
+            raise gd.GdError("the DDPM sampling path runs only on a CUDA device (sm_100a); there is no CPU fallback")
+        self.model, self.diffusion, self.alg = model, diffusion, alg
+        self.N, self.C, self.T = shape
+        self.device = device
+        self.precision = precision
+        self.f32act = precision == "fp32act"
+        self.graph_steps, self.use_graph = graph_steps, use_graph
+        self.L = _Launcher()
+        self.W = model.packed_weights(diffusion, device)
+        if self.C != self.W.C:
+            raise ValueError(f"shape[1]={self.C} does not match the model's d_pose={self.W.C}")
+        self.n_steps = diffusion.num_timesteps
+        self.tabs = [t.to(device).contiguous() for t in diffusion.step_tables(alg)]
+        self.step = th.zeros(1, dtype=th.int32, device=device)
+        self.x = th.zeros(self.N, self.C, self.T, device=device)
+        self.xa = th.zeros(self.N * self.T, _POSE_PAD, device=device, dtype=th.bfloat16)
+        self.eps = th.zeros_like(self.x)
+        self.x0 = th.zeros_like(self.x)
+        self.tape = None
+        self.blend = None
+        self.plan = None
+        self.graph = None
+        self._plan_key = None
+        self.Tm = None
+
+    # ------------------------------------------------------------------ loop-invariant conditioning
+    def _step_token_table(self):
+        """z_t for every loop index: Linear -> SiLU -> Linear on the sinusoidal table (nn.py:41-52), two GEMMs."""
+        W, d, n = self.W, self.W.d, self.n_steps
+        h = th.empty(n, d, device=self.device, dtype=th.bfloat16)
+        zt = th.empty(n, d, device=self.device, dtype=th.bfloat16)
+        self.L.linear(W.t_embed, W.tmlp[0], n, d, d, bias=W.tmlp[1], act=gd.ACT_SILU, out_bf16=h)()
+        self.L.linear(h, W.tmlp[2], n, d, d, bias=W.tmlp[3], out_bf16=zt)()
+        return zt
+
+    def _speech_features(self, wav):
+        enc = self.model.speech_encoder
+        prev = th.backends.cudnn.allow_tf32, th.backends.cuda.matmul.allow_tf32
+        th.backends.cudnn.allow_tf32 = th.backends.cuda.matmul.allow_tf32 = False  # reference math is fp32
+        try:
+            with th.no_grad():
+                return enc(wavform=wav.float())
+        finally:
+            th.backends.cudnn.allow_tf32, th.backends.cuda.matmul.allow_tf32 = prev
+
+    def _conditioning(self, wav):
+        W, d, N, dev = self.W, self.W.d, self.N, self.device
+        z_low, z_mid, z_high = self._speech_features(wav)
+        zt = self._step_token_table()
+        n = self.n_steps
+        if W.kind == "cross_attention":
+            # memory = [z_t ; low ; mid ; high]  (model.py:48-68); positions Tx.. of the joint PE (nn.py:436-442)
+            speech = th.cat([z_low, z_mid, z_high], dim=1)  # (N, Ts, d)
+            Ts = speech.shape[1]
+            Tm = Ts + 1
+            sp16 = speech.reshape(N * Ts, d).to(th.bfloat16).contiguous()
+            emb = th.empty(N * Ts, d, device=dev)
+            self.L.linear(sp16, W.embm_w, N * Ts, d, d, bias=W.embm_b, rowbias=W.pe, period=Ts, offset=self.T + 1,
+                          out_f32=emb)()
+            mem_init = th.zeros(N, Tm, d, device=dev)
+            mem_init[:, 1:] = emb.view(N, Ts, d)
+            mem_tab = th.empty(n, d, device=dev)
+            self.L.linear(zt, W.embm_w, n, d, d, bias=W.embm_b, rowbias=W.pe, period=1, offset=self.T, out_f32=mem_tab)()
+            return {"Tm": Tm, "mem_init": mem_init.view(N * Tm, d), "mem_tab": mem_tab}
+        # oneway: memory = [z_t ; blend(low|mid|high)] -> emb_mem + PE[0..Tm)  (model.py:90-115, nn.py:218-219)
+        longest = max(z_low.shape[1], z_mid.shape[1], z_high.shape[1])
+        pad = lambda z: th.nn.functional.pad(z, (0, 0, longest - z.shape[1], 0))  # noqa: E731  zero rows in front
+        cat16 = th.cat([pad(z_low), pad(z_mid), pad(z_high)], dim=-1).reshape(N * longest, 3 * d).to(th.bfloat16).contiguous()
+        z16 = th.empty(N * longest, d, device=dev, dtype=th.bfloat16)
+        self.L.linear(cat16, W.blend_w, N * longest, d, 3 * d, bias=W.blend_b, out_bf16=z16)()
+        Tm = longest + 1
+        mem16 = th.zeros(N, Tm, d, device=dev, dtype=th.bfloat16)
+        mem16[:, 1:] = z16.view(N, longest, d)
+        memE = th.empty(N * Tm, d, device=dev, dtype=th.bfloat16)  # emb_mem(memory)+PE, bf16 operand of the K|V GEMM
+        self.L.linear(mem16.view(N * Tm, d), W.embm_w, N * Tm, d, d, bias=W.embm_b, rowbias=W.pe, period=Tm, offset=0,
+                      out_bf16=memE)()
+        row0 = th.empty(n, d, device=dev, dtype=th.bfloat16)
+        self.L.linear(zt, W.embm_w, n, d, d, bias=W.embm_b, rowbias=W.pe, period=1, offset=0, out_bf16=row0)()
+        width = W.n_layers * 2 * d
+        kv_dt = th.float32 if self.f32act else th.bfloat16
+        kv = th.empty(N * Tm, width, device=dev, dtype=kv_dt)
+        kv0 = th.empty(n, width, device=dev, dtype=kv_dt)
+        okw = "out_f32" if self.f32act else "out_bf16"
+        self.L.linear(memE, W.ca_wkv, N * Tm, width, d, bias=W.ca_bkv, **{okw: kv})()
+        self.L.linear(row0, W.ca_wkv, n, width, d, bias=W.ca_bkv, **{okw: kv0})()
+        return {"Tm": Tm, "kv": kv, "kv0": kv0}
+
+    # ------------------------------------------------------------------ per-step plan
+    def _ddpm_desc(self):
+        u = gd.DdpmDesc()
+        u.x = _p(self.x)
+        u.noise_tape = _p(self.tape)
+        u.coef_A, u.coef_B, u.coef_C1, u.coef_C2, u.sigma = [_p(t) for t in self.tabs]
+        u.step_ptr = _p(self.step)
+        u.n_clips, u.C, u.T = self.N, self.C, self.T
+        u.eps_out, u.x0_out = _p(self.eps), _p(self.x0)
+        u.xa_bf16, u.ld_xa = _p(self.xa), _POSE_PAD
+        if self.blend is not None:
+            u.inpaint_seed, u.inpaint_mask, u.inpaint_factor = _p(self.blend.seed), _p(self.blend.mask), _p(self.blend.factor)
+        u.clip_x0 = 0.0
+        return u
+
+    def _attn_block(self, ops, a, rows_lo, rows_hi, segs, xn, qkv, ao, H, n_heads):
+        """LN'd rows [lo,hi) -> fused QKV GEMM -> dconv attention over `segs` -> out-proj + residual into H."""
+        d, L = self.W.d, self.L
+        M = rows_hi - rows_lo
+        okw = "out_f32" if self.f32act else "out_bf16"
+        ops.append(L.linear(xn[rows_lo:rows_hi], a["wqkv"], M, 3 * d, d, bias=a["bqkv"], **{okw: qkv[rows_lo:rows_hi]}))
+        q = [(qkv[lo:, 0:], r) for lo, r in segs]
+        k = [(qkv[lo:, d:], r) for lo, r in segs]
+        v = [(qkv[lo:, 2 * d:], r) for lo, r in segs]
+        o = [(ao[lo:], r) for lo, r in segs]
+        ops.append(L.attention(self.N, n_heads, d // n_heads, q, k, v, o, a["taps"], self.f32act))
+        ops.append(L.linear(ao[rows_lo:rows_hi], a["wo"], M, d, d, bias=a["bo"], residual=H[rows_lo:rows_hi],
+                            out_f32=H[rows_lo:rows_hi]))
+
+    def _ffn_block(self, ops, f, ln, lo, hi, xn, hid, H):
+        d, L = self.W.d, self.L
+        M = hi - lo
+        ops.append(L.layernorm(H[lo:hi], ln, xn[lo:hi], M, d))
+        ops.append(L.linear(xn[lo:hi], f["w1"], M, 4 * d, d, bias=f["b1"], act=gd.ACT_RELU2, out_bf16=hid[lo:hi]))
+        ops.append(L.linear(hid[lo:hi], f["w2"], M, d, 4 * d, bias=f["b2"], residual=H[lo:hi], out_f32=H[lo:hi]))
+
+    def _build_plan(self, cond):
+        W, L, N, T, d, dev = self.W, self.L, self.N, self.T, self.W.d, self.device
+        heads, lib = W.heads, self.L.lib
+        Tm = cond["Tm"]
+        Mx = N * T
+        ops = []
+        qkv_dt = th.float32 if self.f32act else th.bfloat16
+        if W.kind == "cross_attention":
+            Mm = N * Tm
+            R = Mx + Mm
+            H = th.empty(R, d, device=dev)
+            xn = th.empty(R, d, device=dev, dtype=th.bfloat16)
+            qkv = th.empty(R, 3 * d, device=dev, dtype=qkv_dt)
+            ao = th.empty(R, d, device=dev, dtype=th.bfloat16)
+            hid = th.empty(R, 4 * d, device=dev, dtype=th.bfloat16)
+            X, Mem = H[:Mx], H[Mx:]
+            a_sc = (_p(Mem), _p(cond["mem_init"]), _p(cond["mem_tab"]), _p(self.step), N, Tm, 0, d, d)
+            ops.append(lambda: gd.check(lib.gd_scatter_step_row_f32(*a_sc, L.stream()), "gd_scatter_step_row_f32"))
+            ops.append(L.linear(self.xa, W.embx_w, Mx, d, _POSE_PAD, bias=W.embx_b, rowbias=W.pe, period=T, offset=0, out_f32=X))
+            for li, ly in enumerate(W.layers):
+                last = li == W.n_layers - 1
+                ops.append(L.layernorm(X, ly["ln_sa"], xn[:Mx], Mx, d))
+                self._attn_block(ops, ly["sa"], 0, Mx, [(0, T)], xn, qkv, ao, H, heads)
+                ops.append(L.layernorm(Mem, ly["ln_sam"], xn[Mx:], Mm, d))
+                self._attn_block(ops, ly["sam"], Mx, R, [(Mx, Tm)], xn, qkv, ao, H, heads)
+                # joint attention over [x ; memory] (nn.py:105-113); last layer only the pose rows are read afterwards
+                ops.append(L.layernorm(H, ly["ln_ca"], xn, R, d))
+                a = ly["ca"]
+                okw = "out_f32" if self.f32act else "out_bf16"
+                ops.append(L.linear(xn, a["wqkv"], R, 3 * d, d, bias=a["bqkv"], **{okw: qkv}))
+                segs = [(0, T), (Mx, Tm)]
+                qs = [(qkv[lo:, 0:], r) for lo, r in (segs[:1] if last else segs)]
+                os_ = [(ao[lo:], r) for lo, r in (segs[:1] if last else segs)]
+                ks = [(qkv[lo:, d:], r) for lo, r in segs]
+                vs = [(qkv[lo:, 2 * d:], r) for lo, r in segs]
+                ops.append(L.attention(N, heads, d // heads, qs, ks, vs, os_, a["taps"], self.f32act))
+                Ro = Mx if last else R
+                ops.append(L.linear(ao[:Ro], a["wo"], Ro, d, d, bias=a["bo"], residual=H[:Ro], out_f32=H[:Ro]))
+                self._ffn_block(ops, ly["ff"], ly["ln_ff"], 0, Mx, xn, hid, H)
+                if "ffm" in ly:
+                    self._ffn_block(ops, ly["ffm"], ly["ln_ffm"], Mx, R, xn, hid, H)
+        else:
+            X = th.empty(Mx, d, device=dev)
+            H = X
+            xn = th.empty(Mx, d, device=dev, dtype=th.bfloat16)
+            qkv = th.empty(Mx, 3 * d, device=dev, dtype=qkv_dt)
+            ao = th.empty(Mx, d, device=dev, dtype=th.bfloat16)
+            hid = th.empty(Mx, 4 * d, device=dev, dtype=th.bfloat16)
+            kv, kv0 = cond["kv"], cond["kv0"]
+            width = kv.shape[1]
+            if self.f32act:
+                a_sc = (_p(kv), None, _p(kv0), _p(self.step), N, Tm, 0, width, width)
+                ops.append(lambda: gd.check(lib.gd_scatter_step_row_f32(*a_sc, L.stream()), "gd_scatter_step_row_f32"))
+            else:
+                a_sc = (_p(kv), _p(kv0), _p(self.step), N, Tm, 0, width, width)
+                ops.append(lambda: gd.check(lib.gd_scatter_step_row_bf16(*a_sc, L.stream()), "gd_scatter_step_row_bf16"))
+            ops.append(L.linear(self.xa, W.embx_w, Mx, d, _POSE_PAD, bias=W.embx_b, rowbias=W.pe, period=T, offset=0, out_f32=X))
+            okw = "out_f32" if self.f32act else "out_bf16"
+            for li, ly in enumerate(W.layers):
+                ops.append(L.layernorm(X, ly["ln_sa"], xn, Mx, d))
+                self._attn_block(ops, ly["sa"], 0, Mx, [(0, T)], xn, qkv, ao, H, heads)
+                # cross attention: queries from the pose rows, K|V hoisted per chain (memory is never updated, nn.py:160-162)
+                a = ly["ca"]
+                ops.append(L.layernorm(X, ly["ln_ca"], xn, Mx, d))
+                ops.append(L.linear(xn, a["wqkv"][:d], Mx, d, d, bias=a["bqkv"][:d], **{okw: qkv[:, :d]}))
+                kcol = li * 2 * d
+                ops.append(L.attention(N, heads, d // heads, [(qkv[:, 0:], T)], [(kv[:, kcol:], Tm)], [(kv[:, kcol + d:], Tm)],
+                                       [(ao, T)], a["taps"], self.f32act))
+                ops.append(L.linear(ao, a["wo"], Mx, d, d, bias=a["bo"], residual=X, out_f32=X))
+                self._ffn_block(ops, ly["ff"], ly["ln_ff"], 0, Mx, xn, hid, H)
+        ops.append(L.layernorm(X, W.out_ln, xn[:Mx], Mx, d))
+        dd = gd.LinearDesc()
+        dd.A, dd.W, dd.M, dd.N, dd.K, dd.lda, dd.ldw, dd.bias = _p(xn), _p(W.out_w), Mx, _POSE_PAD, d, d, d, _p(W.out_b)
+        self._ddpm = self._ddpm_desc()
+        ops.append(lambda: gd.check(lib.gd_linear_ddpm(C.byref(dd), C.byref(self._ddpm), L.stream()), "gd_linear_ddpm"))
+        a_st = (_p(self.step), -1)
+        ops.append(lambda: gd.check(lib.gd_step_add(*a_st, L.stream()), "gd_step_add"))
+        self._buffers = (H, xn, qkv, ao, hid, cond)
+        return ops
+
+    # ------------------------------------------------------------------ public driver
+    def begin(self, x_T, wav, denoise_fn=None, noise_tape=None, need_tape=True):
+        """Load x_T, compute the conditioning once, (re)build the plan, reset the step counter."""
+        from .diffusion import InpaintBlend
+        if denoise_fn is not None and not isinstance(denoise_fn, InpaintBlend):
+            raise NotImplementedError("denoise_fn must be an InpaintBlend (the fused in-paint epilogue); "
+                                      "arbitrary Python closures cannot run inside the captured chain")
+        if tuple(x_T.shape) != (self.N, self.C, self.T):
+            raise ValueError(f"noise shape {tuple(x_T.shape)} != {(self.N, self.C, self.T)}")
+        assert wav.dim() == 2 and wav.shape[0] == self.N, f"Wav dim should be (N,T). Got: {tuple(wav.shape)}"
+        dev = self.device
+        tape_shape = (self.n_steps, self.N, self.C, self.T)
+        if need_tape:
+            if noise_tape is None:
+                # the reference draws one randn_like per step in loop order (gaussian_diffusion.py:326); same calls,
+                # same generator stream.  Loop position k uses index i = n-1-k.
+                if self.tape is None or self.tape.shape != tape_shape:
+                    self.tape = th.empty(tape_shape, device=dev)
+                for k in range(self.n_steps):
+                    self.tape[self.n_steps - 1 - k] = th.randn_like(self.x)
+            else:
+                assert tuple(noise_tape.shape) == tape_shape, f"noise_tape must be {tape_shape}"
+                tp = noise_tape.to(dev).float().flip(0).contiguous()  # loop order -> index order
+                if self.tape is not None and self.tape.shape == tape_shape:
+                    self.tape.copy_(tp)
+                else:
+                    self.tape = tp
+        blend_key = None if denoise_fn is None else "blend"
+        cond = self._conditioning(wav)
+        key = (cond["Tm"], blend_key, need_tape, _p(self.tape) if need_tape else 0)
+        if self.plan is None or key != self._plan_key:
+            self.blend = denoise_fn
+            self.Tm = cond["Tm"]
+            if not need_tape:
+                self.tape = None
+            self.plan = self._build_plan(cond)
+            self._plan_key, self.graph = key, None
+        else:
+            # same plan/graph: refresh the buffers the captured kernels read
+            old = self._buffers[5]
+            for name, val in cond.items():
+                if isinstance(val, th.Tensor):
+                    old[name].copy_(val)
+            if denoise_fn is not None:
+                self.blend.seed.copy_(denoise_fn.seed)
+                self.blend.mask.copy_(denoise_fn.mask)
+                self.blend.factor.copy_(denoise_fn.factor)
+        self.x.copy_(x_T.float())
+        gd.check(self.L.lib.gd_pack_pose_rows(_p(self.x), _p(self.xa), self.N, self.C, self.T, _POSE_PAD, self.L.stream()),
+                 "gd_pack_pose_rows")
+        self.step.fill_(self.n_steps - 1)
+
+    def step_eager(self):
+        for op in self.plan:
+            op()
+
+    def set_state(self, x, i):
+        """Teacher forcing: overwrite the sample and the loop index (parity harness)."""
+        self.x.copy_(x.to(self.device).float())
+        gd.check(self.L.lib.gd_pack_pose_rows(_p(self.x), _p(self.xa), self.N, self.C, self.T, _POSE_PAD, self.L.stream()),
+                 "gd_pack_pose_rows")
+        self.step.fill_(int(i))
+
+    def _ensure_graph(self):
+        if self.graph is not None or not self.use_graph:
+            return
+        # one eager step on a side stream warms every kernel (func attributes, tensor-map encode path)
+        saved = (self.x.clone(), self.xa.clone(), self.step.clone())
+        s = th.cuda.Stream(device=self.device)
+        s.wait_stream(th.cuda.current_stream())
+        with th.cuda.stream(s):
+            self.step_eager()
+        th.cuda.current_stream().wait_stream(s)
+        th.cuda.synchronize()
+        self.x.copy_(saved[0]); self.xa.copy_(saved[1]); self.step.copy_(saved[2])
+        g = th.cuda.CUDAGraph()
+        with th.cuda.graph(g):
+            for _ in range(self.graph_steps):
+                self.step_eager()
+        self.x.copy_(saved[0]); self.xa.copy_(saved[1]); self.step.copy_(saved[2])
+        self.graph = g
+
+    def _result(self):
+        return {"sample": self.x, "eps": self.eps, "pred_x_start": self.x0}
+
+    def run(self, progress=False, n_steps=None):
+        """Run the remaining chain (or `n_steps` steps). Returns the last step's dict."""
+        total = self.n_steps if n_steps is None else n_steps
+        if self.use_graph:
+            self._ensure_graph()
+            done = 0
+            while total - done >= self.graph_steps:
+                self.graph.replay()
+                done += self.graph_steps
+            for _ in range(total - done):
+                self.step_eager()
+        else:
+            for _ in range(total):
+                self.step_eager()
+        return self._result()
+
+    def iterate(self, progress=False):
+        """Progressive form (p_sample_loop_progressive): yields cloned per-step dicts."""
+        for _ in range(self.n_steps):
+            self.step_eager()
+            yield {k: v.clone() for k, v in self._result().items()}
+
+
+_CHAINS = {}
+
+
+def chain_for(model, diffusion, shape, alg, device, **kw):
+    """Cache of sampling contexts keyed by (model, diffusion, shape, algorithm): buffers and graphs are reused."""
+    device = th.device(device)
+    if device.type == "cuda" and device.index is None:
+        device = th.device("cuda", th.cuda.current_device())
+    opts = dict(precision=getattr(model, "precision", "bf16"), graph_steps=getattr(model, "graph_steps", 1),
+                use_graph=getattr(model, "use_graph", True))
+    opts.update(kw)
+    key = (id(model), id(diffusion), shape, alg, str(device), model.weights_version, tuple(sorted(opts.items())))
+    ch = _CHAINS.get(key)
+    if ch is None:
+        for k in [k for k in _CHAINS if k[0] == id(model) and k[2] != shape]:
+            del _CHAINS[k]  # keep one batch shape per model resident
+        ch = SamplingChain(model, diffusion, shape, alg, device, **opts)
+        _CHAINS[key] = ch
+    return ch
