@@ -1,15 +1,22 @@
-// MultiDConvHeadAttention core (reference transformer.py:19-44,88-126) as one fused kernel:
-// depth-wise conv3 over tokens of the projected Q/K/V rows (prologue, straight from HBM with the
-// +-1 token halo), scores, softmax over keys, P·V — one CTA per (clip, head), the whole head in
-// shared memory, single pass (every K/V of a clip fits: <= 160 keys), warp-level softmax.
-// v1 computes on the CUDA cores in fp32; inputs are bf16 (default) or fp32 (fp32-activation path).
+// MultiDConvHeadAttention core (reference transformer.py:19-44,88-126) as one fused kernel.
+//
+// One CTA per (clip, head).  Prologue: the depth-wise conv3 over tokens is applied while the projected Q/K/V rows
+// are staged HBM -> shared memory (16-byte loads, each raw row read ~1.25x thanks to 8-token segments with a
+// +-1 halo held in registers), results rounded to bf16.  Main loop: every warp owns 16-query tiles; S = Q·Kᵀ on
+// the tensor cores (mma.sync m16n8k16 bf16, fragments via ldmatrix), softmax over keys entirely in registers
+// (quad shuffles, exp2 with the scale folded in), then O = P·V with P re-used straight from the accumulator
+// registers as the A fragment (no shared-memory round trip) and V read through ldmatrix.trans.
+// All K/V of a head fit in shared memory (<= 160 keys), so this is single-pass: no running-max rescale.
+// The token sequence of a clip is the concatenation of up to two row segments; the conv runs across the seam
+// (tedexp joint attention over [x ; memory], nn.py:105-113) and zero-pads only at the sequence ends.
 #include "common.cuh"
 #include "host_util.h"
 
 namespace gd {
 
-constexpr int ATT_THREADS = 256;
+constexpr int ATT_THREADS = 128;
 constexpr int ATT_WARPS = ATT_THREADS / 32;
+constexpr int SEG = 8;  // tokens per conv work item
 
 struct AttnParams {
     const void* q[2];
@@ -18,125 +25,250 @@ struct AttnParams {
     __nv_bfloat16* out[2];
     int q_rows[2], q_ld[2], kv_rows[2], kv_ld[2], out_ld[2];
     const float *wq, *bq, *wk, *bk, *wv, *bv;
-    int heads, d_k, Lq, Lk, Lk_pad;
-    float scale;
+    int heads, Lq, Lk;
+    float scale_log2;  // d_k^-1/2 * log2(e)
 };
 
+// 8 consecutive elements of a projected row as fp32
 template <typename T>
-__device__ __forceinline__ float ld_elem(const T* p);
+__device__ __forceinline__ void load8(const T* p, float (&f)[8]);
 template <>
-__device__ __forceinline__ float ld_elem<float>(const float* p) {
-    return *p;
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
 }
 template <>
-__device__ __forceinline__ float ld_elem<__nv_bfloat16>(const __nv_bfloat16* p) {
-    return __bfloat162float(*p);
+__device__ __forceinline__ void load8<float>(const float* p, float (&f)[8]) {
+    const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+    f[0] = a.x, f[1] = a.y, f[2] = a.z, f[3] = a.w, f[4] = b.x, f[5] = b.y, f[6] = b.z, f[7] = b.w;
 }
 
-// raw (pre-conv) element of token `pos` of the concatenated per-clip sequence; 0 outside [0, L).
 template <typename T>
-__device__ __forceinline__ float raw_token(const void* const (&seg)[2], const int (&rows)[2], const int (&ld)[2],
-                                           int clip, int pos, int L, int col) {
-    if (pos < 0 || pos >= L) return 0.f;
-    if (pos < rows[0]) return ld_elem<T>(reinterpret_cast<const T*>(seg[0]) + ((size_t)clip * rows[0] + pos) * ld[0] + col);
-    return ld_elem<T>(reinterpret_cast<const T*>(seg[1]) + ((size_t)clip * rows[1] + (pos - rows[0])) * ld[1] + col);
+__device__ __forceinline__ void raw_row8(const void* const (&seg)[2], const int (&rows)[2], const int (&ld)[2], int clip,
+                                         int pos, int L, int col, float (&f)[8]) {
+    if (pos < 0 || pos >= L) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = 0.f;
+        return;
+    }
+    const T* p = (pos < rows[0])
+                     ? reinterpret_cast<const T*>(seg[0]) + ((size_t)clip * rows[0] + pos) * ld[0] + col
+                     : reinterpret_cast<const T*>(seg[1]) + ((size_t)clip * rows[1] + (pos - rows[0])) * ld[1] + col;
+    load8<T>(p, f);
 }
 
-template <typename T>
-__device__ __forceinline__ void conv_into_smem(float* dst, int stride, const void* const (&seg)[2],
-                                               const int (&rows)[2], const int (&ld)[2], int clip, int head, int L,
-                                               int d_k, const float* w, const float* b) {
-    for (int i = threadIdx.x; i < L * d_k; i += ATT_THREADS) {
-        const int c = i % d_k, pos = i / d_k;
-        const int col = head * d_k + c;
-        const float a0 = raw_token<T>(seg, rows, ld, clip, pos - 1, L, col);
-        const float a1 = raw_token<T>(seg, rows, ld, clip, pos, L, col);
-        const float a2 = raw_token<T>(seg, rows, ld, clip, pos + 1, L, col);
-        dst[pos * stride + c] = __ldg(w + c * 3 + 0) * a0 + __ldg(w + c * 3 + 1) * a1 + __ldg(w + c * 3 + 2) * a2 + __ldg(b + c);
+// dst[pos][c] = bf16( w[c][0]*raw[pos-1][c] + w[c][1]*raw[pos][c] + w[c][2]*raw[pos+1][c] + b[c] ), rows >= L zeroed
+template <typename T, int DK>
+__device__ __forceinline__ void conv_stage(__nv_bfloat16* dst, int L, int L_pad, const void* const (&seg)[2],
+                                           const int (&rows)[2], const int (&ld)[2], int clip, int head,
+                                           const float* s_taps /* [DK*3] */, const float* s_bias /* [DK] */) {
+    constexpr int STR = DK + 8;
+    constexpr int CH = DK / 8;
+    const int n_seg = (L_pad + SEG - 1) / SEG;
+    for (int item = threadIdx.x; item < n_seg * CH; item += ATT_THREADS) {
+        const int ch = item % CH, sg = item / CH;
+        const int c0 = ch * 8, p0 = sg * SEG;
+        float w0[8], w1[8], w2[8], bb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            w0[i] = s_taps[(c0 + i) * 3 + 0];
+            w1[i] = s_taps[(c0 + i) * 3 + 1];
+            w2[i] = s_taps[(c0 + i) * 3 + 2];
+            bb[i] = s_bias[c0 + i];
+        }
+        float prev[8], cur[8], nxt[8];
+        raw_row8<T>(seg, rows, ld, clip, p0 - 1, L, head * DK + c0, prev);
+        raw_row8<T>(seg, rows, ld, clip, p0, L, head * DK + c0, cur);
+#pragma unroll
+        for (int s = 0; s < SEG; ++s) {
+            const int pos = p0 + s;
+            if (pos >= L_pad) break;
+            raw_row8<T>(seg, rows, ld, clip, pos + 1, L, head * DK + c0, nxt);
+            uint4 o = make_uint4(0, 0, 0, 0);
+            if (pos < L) {
+                float r[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r[i] = w0[i] * prev[i] + w1[i] * cur[i] + w2[i] * nxt[i] + bb[i];
+                o.x = pack_bf16x2(r[0], r[1]);
+                o.y = pack_bf16x2(r[2], r[3]);
+                o.z = pack_bf16x2(r[4], r[5]);
+                o.w = pack_bf16x2(r[6], r[7]);
+            }
+            *reinterpret_cast<uint4*>(dst + pos * STR + c0) = o;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                prev[i] = cur[i];
+                cur[i] = nxt[i];
+            }
+        }
     }
 }
 
-template <typename T, int DK>
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// KB = number of 16-key blocks (keys padded to 16*KB), DK = head width
+template <typename T, int DK, int KB>
 __global__ void __launch_bounds__(ATT_THREADS) dconv_attention_kernel(const AttnParams p) {
-    extern __shared__ float sm[];
-    constexpr int STR = DK + 1;  // +1 float: conflict-free row-strided reads
-    float* sq = sm;
-    float* sk = sq + p.Lq * STR;
-    float* sv = sk + p.Lk * STR;
-    float* sp = sv + p.Lk * STR;  // [ATT_WARPS][Lk_pad] probabilities
+    constexpr int STR = DK + 8;  // bf16 elements per smem row: +16 B keeps ldmatrix rows on distinct banks
+    constexpr int LK_PAD = KB * 16;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int Lq_pad = (p.Lq + 15) & ~15;
+    __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+    __nv_bfloat16* sk = sq + Lq_pad * STR;
+    __nv_bfloat16* sv = sk + LK_PAD * STR;
+    float* s_taps = reinterpret_cast<float*>(sv + LK_PAD * STR);  // [3][DK*3 + DK]
     const int clip = blockIdx.x / p.heads, head = blockIdx.x % p.heads;
-    conv_into_smem<T>(sq, STR, p.q, p.q_rows, p.q_ld, clip, head, p.Lq, DK, p.wq, p.bq);
-    conv_into_smem<T>(sk, STR, p.k, p.kv_rows, p.kv_ld, clip, head, p.Lk, DK, p.wk, p.bk);
-    conv_into_smem<T>(sv, STR, p.v, p.kv_rows, p.kv_ld, clip, head, p.Lk, DK, p.wv, p.bv);
+
+    for (int i = threadIdx.x; i < 3 * DK * 4; i += ATT_THREADS) {
+        const int which = i / (DK * 4), j = i % (DK * 4);
+        const float* w = which == 0 ? p.wq : (which == 1 ? p.wk : p.wv);
+        const float* b = which == 0 ? p.bq : (which == 1 ? p.bk : p.bv);
+        s_taps[i] = j < DK * 3 ? __ldg(w + j) : __ldg(b + j - DK * 3);
+    }
+    __syncthreads();
+    conv_stage<T, DK>(sq, p.Lq, Lq_pad, p.q, p.q_rows, p.q_ld, clip, head, s_taps, s_taps + DK * 3);
+    conv_stage<T, DK>(sk, p.Lk, LK_PAD, p.k, p.kv_rows, p.kv_ld, clip, head, s_taps + DK * 4, s_taps + DK * 7);
+    conv_stage<T, DK>(sv, p.Lk, LK_PAD, p.v, p.kv_rows, p.kv_ld, clip, head, s_taps + DK * 8, s_taps + DK * 11);
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* prow = sp + warp * p.Lk_pad;
-    constexpr int MAXJ = 5;  // <= 160 keys
-    for (int i = warp; i < p.Lq; i += ATT_WARPS) {
-        const float* qi = sq + i * STR;
-        float s[MAXJ];
-        float mx = -INFINITY;
+    const int g = lane >> 2, t = lane & 3;
+    const uint32_t sq_u = smem_u32(sq), sk_u = smem_u32(sk), sv_u = smem_u32(sv);
+
+    for (int qt = warp; qt * 16 < p.Lq; qt += ATT_WARPS) {
+        // ---- S = Q Kᵀ : 16 x LK_PAD, fp32 accumulators in registers
+        float s[KB * 2][4];
 #pragma unroll
-        for (int jj = 0; jj < MAXJ; ++jj) {
-            const int j = jj * 32 + lane;
-            s[jj] = -INFINITY;
-            if (j < p.Lk) {
-                const float* kj = sk + j * STR;
-                float acc = 0.f;
-#pragma unroll 8
-                for (int c = 0; c < DK; ++c) acc = fmaf(qi[c], kj[c], acc);
-                s[jj] = acc * p.scale;
+        for (int n = 0; n < KB * 2; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < DK / 16; ++kk) {
+            uint32_t a0, a1, a2, a3;
+            ldsm_x4(sq_u + ((qt * 16 + (lane & 15)) * STR + kk * 16 + (lane >> 4) * 8) * 2, a0, a1, a2, a3);
+#pragma unroll
+            for (int nb = 0; nb < KB; ++nb) {
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4(sk_u + ((nb * 16 + (lane & 7) + (lane >> 4) * 8) * STR + kk * 16 + ((lane >> 3) & 1) * 8) * 2, b0, b1,
+                        b2, b3);
+                mma_bf16_16816(s[2 * nb], a0, a1, a2, a3, b0, b1);
+                mma_bf16_16816(s[2 * nb + 1], a0, a1, a2, a3, b2, b3);
             }
-            mx = fmaxf(mx, s[jj]);
         }
-        mx = warp_max(mx);
-        float sum = 0.f;
+        // ---- softmax over keys (rows g and g+8 of the tile), padded keys masked
+        float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-        for (int jj = 0; jj < MAXJ; ++jj) {
-            const int j = jj * 32 + lane;
-            const float e = (j < p.Lk) ? __expf(s[jj] - mx) : 0.f;
-            s[jj] = e;
-            sum += e;
+        for (int n = 0; n < KB * 2; ++n) {
+            const int j = n * 8 + 2 * t;
+            if (j >= p.Lk) s[n][0] = s[n][2] = -INFINITY;
+            if (j + 1 >= p.Lk) s[n][1] = s[n][3] = -INFINITY;
+            m0 = fmaxf(m0, fmaxf(s[n][0], s[n][1]));
+            m1 = fmaxf(m1, fmaxf(s[n][2], s[n][3]));
         }
-        const float inv = 1.0f / warp_sum(sum);
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        const float o0 = m0 * p.scale_log2, o1 = m1 * p.scale_log2;
+        float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-        for (int jj = 0; jj < MAXJ; ++jj) {
-            const int j = jj * 32 + lane;
-            if (j < p.Lk) prow[j] = s[jj] * inv;
+        for (int n = 0; n < KB * 2; ++n) {
+            s[n][0] = exp2f(s[n][0] * p.scale_log2 - o0);
+            s[n][1] = exp2f(s[n][1] * p.scale_log2 - o0);
+            s[n][2] = exp2f(s[n][2] * p.scale_log2 - o1);
+            s[n][3] = exp2f(s[n][3] * p.scale_log2 - o1);
+            sum0 += s[n][0] + s[n][1];
+            sum1 += s[n][2] + s[n][3];
         }
-        __syncwarp();
-        float o[DK / 32];
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+        // ---- O = P V : P comes straight from the accumulators (C layout of two n-tiles == A layout of one k-block)
+        float o[DK / 8][4];
 #pragma unroll
-        for (int r = 0; r < DK / 32; ++r) o[r] = 0.f;
-        for (int j = 0; j < p.Lk; ++j) {
-            const float pj = prow[j];
+        for (int n = 0; n < DK / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
 #pragma unroll
-            for (int r = 0; r < DK / 32; ++r) o[r] = fmaf(pj, sv[j * STR + r * 32 + lane], o[r]);
+        for (int kb = 0; kb < KB; ++kb) {
+            const uint32_t a0 = pack_bf16x2(s[2 * kb][0], s[2 * kb][1]), a1 = pack_bf16x2(s[2 * kb][2], s[2 * kb][3]);
+            const uint32_t a2 = pack_bf16x2(s[2 * kb + 1][0], s[2 * kb + 1][1]), a3 = pack_bf16x2(s[2 * kb + 1][2], s[2 * kb + 1][3]);
+#pragma unroll
+            for (int nb = 0; nb < DK / 16; ++nb) {
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4_trans(sv_u + ((kb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * STR + nb * 16 + (lane >> 4) * 8) * 2, b0,
+                              b1, b2, b3);
+                mma_bf16_16816(o[2 * nb], a0, a1, a2, a3, b0, b1);
+                mma_bf16_16816(o[2 * nb + 1], a0, a1, a2, a3, b2, b3);
+            }
         }
-        __syncwarp();
-        __nv_bfloat16* orow = (i < p.q_rows[0])
-                                  ? p.out[0] + ((size_t)clip * p.q_rows[0] + i) * p.out_ld[0]
-                                  : p.out[1] + ((size_t)clip * p.q_rows[1] + (i - p.q_rows[0])) * p.out_ld[1];
+        const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
 #pragma unroll
-        for (int r = 0; r < DK / 32; ++r) orow[head * DK + r * 32 + lane] = __float2bfloat16_rn(o[r]);
+        for (int half = 0; half < 2; ++half) {
+            const int i = qt * 16 + g + half * 8;
+            if (i < p.Lq) {
+                __nv_bfloat16* orow = (i < p.q_rows[0])
+                                          ? p.out[0] + ((size_t)clip * p.q_rows[0] + i) * p.out_ld[0]
+                                          : p.out[1] + ((size_t)clip * p.q_rows[1] + (i - p.q_rows[0])) * p.out_ld[1];
+                const float inv = half ? inv1 : inv0;
+#pragma unroll
+                for (int n = 0; n < DK / 8; ++n)
+                    *reinterpret_cast<uint32_t*>(orow + head * DK + n * 8 + 2 * t) =
+                        pack_bf16x2(o[n][2 * half] * inv, o[n][2 * half + 1] * inv);
+            }
+        }
     }
 }
 
-template <typename T, int DK>
+template <typename T, int DK, int KB>
 static int launch_attention(const AttnParams& p, int n_clips, cudaStream_t s) {
-    const size_t smem = ((size_t)(p.Lq + 2 * p.Lk) * (DK + 1) + (size_t)ATT_WARPS * p.Lk_pad) * sizeof(float);
-    if (smem > 227 * 1024) return set_error(GD_ERR_INVALID, "gd_dconv_attention: sequence too long for shared memory");
-    static size_t configured = 0;
+    const int Lq_pad = (p.Lq + 15) & ~15;
+    const size_t smem = (size_t)(Lq_pad + 2 * KB * 16) * (DK + 8) * 2 + 3 * DK * 4 * sizeof(float);
+    static size_t configured = 48 * 1024;
     if (smem > configured) {
-        GD_CUDA_CHECK(cudaFuncSetAttribute(dconv_attention_kernel<T, DK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GD_CUDA_CHECK(cudaFuncSetAttribute(dconv_attention_kernel<T, DK, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem));
         configured = smem;
     }
-    dconv_attention_kernel<T, DK><<<n_clips * p.heads, ATT_THREADS, smem, s>>>(p);
+    dconv_attention_kernel<T, DK, KB><<<n_clips * p.heads, ATT_THREADS, smem, s>>>(p);
     count_launch();
     GD_CUDA_CHECK(cudaGetLastError());
     return GD_OK;
+}
+
+template <typename T, int DK>
+static int dispatch_kb(const AttnParams& p, int n_clips, cudaStream_t s) {
+    switch ((p.Lk + 15) / 16) {
+        case 1: return launch_attention<T, DK, 1>(p, n_clips, s);
+        case 2: return launch_attention<T, DK, 2>(p, n_clips, s);
+        case 3: return launch_attention<T, DK, 3>(p, n_clips, s);
+        case 4: return launch_attention<T, DK, 4>(p, n_clips, s);
+        case 5: return launch_attention<T, DK, 5>(p, n_clips, s);
+        case 6: return launch_attention<T, DK, 6>(p, n_clips, s);
+        case 7: return launch_attention<T, DK, 7>(p, n_clips, s);
+        case 8: return launch_attention<T, DK, 8>(p, n_clips, s);
+        case 9: return launch_attention<T, DK, 9>(p, n_clips, s);
+        case 10: return launch_attention<T, DK, 10>(p, n_clips, s);
+    }
+    return set_error(GD_ERR_INVALID, "gd_dconv_attention: need 0 < keys <= 160 (got %d)", p.Lk);
 }
 
 static int run_attention(const gd_attn_desc* d, bool fp32_in, void* stream) {
@@ -145,24 +277,29 @@ static int run_attention(const gd_attn_desc* d, bool fp32_in, void* stream) {
     if (!d->conv_wq || !d->conv_bq || !d->conv_wk || !d->conv_bk || !d->conv_wv || !d->conv_bv)
         return set_error(GD_ERR_INVALID, "gd_dconv_attention: conv taps missing");
     if (d->n_clips <= 0 || d->heads <= 0) return set_error(GD_ERR_INVALID, "gd_dconv_attention: bad clip/head count");
+    if ((d->q[1] && !d->out[1]) || (d->k[1] && !d->v[1])) return set_error(GD_ERR_INVALID, "gd_dconv_attention: segment 1 incomplete");
     AttnParams p{};
+    const int align = fp32_in ? 4 : 8;  // 16-byte row loads
     for (int s = 0; s < 2; ++s) {
         p.q[s] = d->q[s], p.k[s] = d->k[s], p.v[s] = d->v[s];
         p.out[s] = reinterpret_cast<__nv_bfloat16*>(d->out[s]);
         p.q_rows[s] = d->q[s] ? d->q_rows[s] : 0;
         p.kv_rows[s] = d->k[s] ? d->kv_rows[s] : 0;
         p.q_ld[s] = d->q_ld[s], p.kv_ld[s] = d->kv_ld[s], p.out_ld[s] = d->out_ld[s];
+        if ((d->q[s] && (d->q_ld[s] % align || (reinterpret_cast<uintptr_t>(d->q[s]) & 15) || d->out_ld[s] % 2)) ||
+            (d->k[s] && (d->kv_ld[s] % align || ((reinterpret_cast<uintptr_t>(d->k[s]) | reinterpret_cast<uintptr_t>(d->v[s])) & 15))))
+            return set_error(GD_ERR_INVALID, "gd_dconv_attention: q/k/v rows must be 16-byte aligned");
     }
-    if ((d->q[1] && !d->out[1]) || (d->k[1] && !d->v[1])) return set_error(GD_ERR_INVALID, "gd_dconv_attention: segment 1 incomplete");
     p.wq = d->conv_wq, p.bq = d->conv_bq, p.wk = d->conv_wk, p.bk = d->conv_bk, p.wv = d->conv_wv, p.bv = d->conv_bv;
-    p.heads = d->heads, p.d_k = d->d_k, p.scale = d->scale;
+    p.heads = d->heads;
+    p.scale_log2 = d->scale * 1.4426950408889634f;
     p.Lq = p.q_rows[0] + p.q_rows[1];
     p.Lk = p.kv_rows[0] + p.kv_rows[1];
-    if (p.Lq <= 0 || p.Lk <= 0 || p.Lk > 160) return set_error(GD_ERR_INVALID, "gd_dconv_attention: need 0 < keys <= 160 (got %d)", p.Lk);
-    p.Lk_pad = (p.Lk + 31) & ~31;
+    if (p.Lq <= 0 || p.Lk <= 0 || p.Lk > 160 || p.Lq > 1024)
+        return set_error(GD_ERR_INVALID, "gd_dconv_attention: need 0 < keys <= 160 (got %d), queries <= 1024", p.Lk);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (d->d_k == 32) return fp32_in ? launch_attention<float, 32>(p, d->n_clips, s) : launch_attention<__nv_bfloat16, 32>(p, d->n_clips, s);
-    if (d->d_k == 64) return fp32_in ? launch_attention<float, 64>(p, d->n_clips, s) : launch_attention<__nv_bfloat16, 64>(p, d->n_clips, s);
+    if (d->d_k == 32) return fp32_in ? dispatch_kb<float, 32>(p, d->n_clips, s) : dispatch_kb<__nv_bfloat16, 32>(p, d->n_clips, s);
+    if (d->d_k == 64) return fp32_in ? dispatch_kb<float, 64>(p, d->n_clips, s) : dispatch_kb<__nv_bfloat16, 64>(p, d->n_clips, s);
     return set_error(GD_ERR_INVALID, "gd_dconv_attention: d_k=%d unsupported (32/64)", d->d_k);
 }
 

@@ -99,6 +99,17 @@ class PackedWeights:
         self.n_steps = diffusion.num_timesteps
 
 
+class Op:
+    """One kernel launch of the step plan, with the algorithmic work it performs (bench.py's roofline inputs)."""
+    __slots__ = ("fn", "kind", "flops", "bytes")
+
+    def __init__(self, fn, kind, flops=0, nbytes=0):
+        self.fn, self.kind, self.flops, self.bytes = fn, kind, flops, nbytes
+
+    def __call__(self):
+        self.fn()
+
+
 class _Launcher:
     """Thin typed wrappers over the C-ABI; every call goes to libgd_b200.so on the current torch stream."""
 
@@ -111,7 +122,7 @@ class _Launcher:
         return th.cuda.current_stream().cuda_stream
 
     def linear(self, A, W, M, N, K, bias=None, rowbias=None, period=0, offset=0, residual=None, act=gd.ACT_NONE,
-               out_f32=None, out_bf16=None, lda=None, ldo32=None, ldo16=None):
+               out_f32=None, out_bf16=None, lda=None, ldo32=None, ldo16=None, k_alg=None):
         d = gd.LinearDesc()
         d.A, d.W, d.M, d.N, d.K = _p(A), _p(W), M, N, K
         d.lda, d.ldw = (lda or A.stride(0)), W.stride(0)
@@ -121,12 +132,15 @@ class _Launcher:
         d.out_f32, d.ldo_f32 = _p(out_f32), (ldo32 or (out_f32.stride(0) if out_f32 is not None else 0))
         d.out_bf16, d.ldo_bf16 = _p(out_bf16), (ldo16 or (out_bf16.stride(0) if out_bf16 is not None else 0))
         lib = self.lib
-        return lambda: gd.check(lib.gd_linear_bf16(C.byref(d), self.stream()), "gd_linear_bf16")
+        nbytes = 2 * M * K + 2 * N * K + (4 * M * N if residual is not None else 0) + \
+            (4 * M * N if out_f32 is not None else 0) + (2 * M * N if out_bf16 is not None else 0)
+        return Op(lambda: gd.check(lib.gd_linear_bf16(C.byref(d), self.stream()), "gd_linear_bf16"), "gemm",
+                  2 * M * N * (k_alg or K), nbytes)
 
     def layernorm(self, x, gamma_beta, out, M, D):
         lib, g, b = self.lib, gamma_beta[0], gamma_beta[1]
         args = (_p(x), x.stride(0), _p(g), _p(b), _p(out), out.stride(0), M, D, 1e-5)
-        return lambda: gd.check(lib.gd_layernorm(*args, self.stream()), "gd_layernorm")
+        return Op(lambda: gd.check(lib.gd_layernorm(*args, self.stream()), "gd_layernorm"), "layernorm", 8 * M * D, 6 * M * D)
 
     def attention(self, n_clips, heads, d_k, q, k, v, out, taps, f32in):
         """q/k/v/out: lists of up to two (tensor_view, rows_per_clip) segments; views start at the right column."""
@@ -140,7 +154,10 @@ class _Launcher:
         a.conv_wq, a.conv_bq, a.conv_wk, a.conv_bk, a.conv_wv, a.conv_bv = [_p(t) for t in taps]
         a.n_clips, a.heads, a.d_k, a.scale = n_clips, heads, d_k, 1.0 / math.sqrt(d_k)
         fn = self.lib.gd_dconv_attention_f32in if f32in else self.lib.gd_dconv_attention
-        return lambda: gd.check(fn(C.byref(a), self.stream()), "gd_dconv_attention")
+        Lq, Lk, dm, es = sum(r for _, r in q), sum(r for _, r in k), heads * d_k, (4 if f32in else 2)
+        flops = n_clips * (4 * Lq * Lk * dm + 6 * dm * (Lq + 2 * Lk))  # QK^T + PV + three 3-tap convs
+        nbytes = n_clips * dm * (es * (Lq + 2 * Lk) + 2 * Lq)
+        return Op(lambda: gd.check(fn(C.byref(a), self.stream()), "gd_dconv_attention"), "attention", flops, nbytes)
 
 
 class SamplingChain:
@@ -288,8 +305,10 @@ class SamplingChain:
             hid = th.empty(R, 4 * d, device=dev, dtype=th.bfloat16)
             X, Mem = H[:Mx], H[Mx:]
             a_sc = (_p(Mem), _p(cond["mem_init"]), _p(cond["mem_tab"]), _p(self.step), N, Tm, 0, d, d)
-            ops.append(lambda: gd.check(lib.gd_scatter_step_row_f32(*a_sc, L.stream()), "gd_scatter_step_row_f32"))
-            ops.append(L.linear(self.xa, W.embx_w, Mx, d, _POSE_PAD, bias=W.embx_b, rowbias=W.pe, period=T, offset=0, out_f32=X))
+            ops.append(Op(lambda: gd.check(lib.gd_scatter_step_row_f32(*a_sc, L.stream()), "gd_scatter_step_row_f32"),
+                          "scatter", 0, 8 * Mm * d))
+            ops.append(L.linear(self.xa, W.embx_w, Mx, d, _POSE_PAD, bias=W.embx_b, rowbias=W.pe, period=T, offset=0,
+                                out_f32=X, k_alg=self.C))
             for li, ly in enumerate(W.layers):
                 last = li == W.n_layers - 1
                 ops.append(L.layernorm(X, ly["ln_sa"], xn[:Mx], Mx, d))
@@ -323,11 +342,14 @@ class SamplingChain:
             width = kv.shape[1]
             if self.f32act:
                 a_sc = (_p(kv), None, _p(kv0), _p(self.step), N, Tm, 0, width, width)
-                ops.append(lambda: gd.check(lib.gd_scatter_step_row_f32(*a_sc, L.stream()), "gd_scatter_step_row_f32"))
+                ops.append(Op(lambda: gd.check(lib.gd_scatter_step_row_f32(*a_sc, L.stream()), "gd_scatter_step_row_f32"),
+                              "scatter", 0, 8 * N * width))
             else:
                 a_sc = (_p(kv), _p(kv0), _p(self.step), N, Tm, 0, width, width)
-                ops.append(lambda: gd.check(lib.gd_scatter_step_row_bf16(*a_sc, L.stream()), "gd_scatter_step_row_bf16"))
-            ops.append(L.linear(self.xa, W.embx_w, Mx, d, _POSE_PAD, bias=W.embx_b, rowbias=W.pe, period=T, offset=0, out_f32=X))
+                ops.append(Op(lambda: gd.check(lib.gd_scatter_step_row_bf16(*a_sc, L.stream()), "gd_scatter_step_row_bf16"),
+                              "scatter", 0, 4 * N * width))
+            ops.append(L.linear(self.xa, W.embx_w, Mx, d, _POSE_PAD, bias=W.embx_b, rowbias=W.pe, period=T, offset=0,
+                                out_f32=X, k_alg=self.C))
             okw = "out_f32" if self.f32act else "out_bf16"
             for li, ly in enumerate(W.layers):
                 ops.append(L.layernorm(X, ly["ln_sa"], xn, Mx, d))
@@ -345,9 +367,11 @@ class SamplingChain:
         dd = gd.LinearDesc()
         dd.A, dd.W, dd.M, dd.N, dd.K, dd.lda, dd.ldw, dd.bias = _p(xn), _p(W.out_w), Mx, _POSE_PAD, d, d, d, _p(W.out_b)
         self._ddpm = self._ddpm_desc()
-        ops.append(lambda: gd.check(lib.gd_linear_ddpm(C.byref(dd), C.byref(self._ddpm), L.stream()), "gd_linear_ddpm"))
+        elems = N * self.C * T
+        ops.append(Op(lambda: gd.check(lib.gd_linear_ddpm(C.byref(dd), C.byref(self._ddpm), L.stream()), "gd_linear_ddpm"),
+                      "gemm_ddpm", 2 * Mx * d * self.C, 2 * Mx * d + 2 * _POSE_PAD * d + 4 * elems * 5 + 2 * Mx * _POSE_PAD))
         a_st = (_p(self.step), -1)
-        ops.append(lambda: gd.check(lib.gd_step_add(*a_st, L.stream()), "gd_step_add"))
+        ops.append(Op(lambda: gd.check(lib.gd_step_add(*a_st, L.stream()), "gd_step_add"), "step", 0, 8))
         self._buffers = (H, xn, qkv, ao, hid, cond)
         return ops
 

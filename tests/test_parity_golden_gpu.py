@@ -1,0 +1,87 @@
+"""CUDA sampling path vs golden vectors produced by the REAL reference (CPU fp32) on the full configs:
+per-step teacher-forced eps, bit-level update, the full 1000-step chain, respaced and in-painted chains."""
+import pytest
+import torch as th
+
+from util import build, load_golden, noise_tape, rel_l2, synthetic_wav
+
+pytestmark = pytest.mark.gpu
+
+EPS_TOL = {"bf16": 2e-2, "fp32act": 1e-2}   # per-step teacher-forced eps, rel-L2
+POSE_TOL = {"bf16": 2e-2, "fp32act": 1e-2}  # final pose after the whole chain, rel-L2
+
+
+@pytest.mark.parametrize("name", ["beat", "tedexp"])
+@pytest.mark.parametrize("precision", ["bf16", "fp32act"])
+@pytest.mark.parametrize("weights", ["init", "boost"])
+def test_teacher_forced_steps_vs_reference(name, precision, weights):
+    from gesture_b200.engine import chain_for
+    g = load_golden(name)
+    N = 2
+    model, diffusion, C, T, L, params = build(name, weights, device="cuda")
+    model.precision = precision
+    wav = synthetic_wav(N, L, seed=123)
+    x_T, tape = noise_tape((N, C, T), 1000, seed=99)
+    chain = chain_for(model, diffusion, (N, C, T), "ddpm", "cuda", use_graph=False)
+    chain.begin(x_T.cuda(), wav.cuda(), noise_tape=tape.cuda())
+    for i in (999, 998, 500, 20, 1, 0):
+        chain.set_state(th.from_numpy(g[f"{weights}.ddpm.x_in.{i}"]).cuda(), i)
+        chain.step_eager()
+        th.cuda.synchronize()
+        err = rel_l2(chain.eps, g[f"{weights}.ddpm.eps.{i}"])
+        assert err < EPS_TOL[precision], f"{name}/{weights}/{precision} i={i}: eps rel-L2 {err:.3e}"
+        # x_{t-1}: eps error is scaled by B*C1 in the update; compare against the reference's own next sample
+        errx = rel_l2(chain.x, g[f"{weights}.ddpm.x_out.{i}"])
+        assert errx < EPS_TOL[precision], f"{name}/{weights}/{precision} i={i}: x_next rel-L2 {errx:.3e}"
+
+
+@pytest.mark.parametrize("name", ["beat", "tedexp"])
+@pytest.mark.parametrize("precision", ["bf16", "fp32act"])
+def test_full_chain_vs_reference(name, precision):
+    """The whole 1000-step ancestral chain through Generator.generate_sample (CUDA-graph replays) against the
+    reference's final poses, same weights / speech / x_T / noise tape."""
+    from gesture_b200.generator import Generator
+    g = load_golden(name)
+    N = 2
+    for weights in ("boost", "init"):
+        model, diffusion, C, T, L, params = build(name, weights, device="cuda")
+        model.precision = precision
+        wav = synthetic_wav(N, L, seed=123)
+        x_T, tape = noise_tape((N, C, T), 1000, seed=99)
+        out = Generator(model, diffusion).generate_sample((N, C, T), wav, noise=x_T, sample_alg="ddpm", device="cuda",
+                                                          progress=False, noise_tape=tape)
+        err = rel_l2(out, g[f"{weights}.ddpm.final"])
+        print(f"[{name}/{weights}/{precision}] final pose rel-L2 vs reference: {err:.3e}")
+        assert err < POSE_TOL[precision], f"{name}/{weights}/{precision}: final pose rel-L2 {err:.3e}"
+
+
+@pytest.mark.parametrize("name", ["beat", "tedexp"])
+def test_respaced_and_inpaint_chains_vs_reference(name):
+    from gesture_b200.generator import Generator
+    g = load_golden(name)
+    N = 2
+    model, diffusion, C, T, L, params = build(name, "boost", respacing="ddim50", device="cuda")
+    gen = Generator(model, diffusion)
+    wav = synthetic_wav(N, L, seed=123)
+    x_T, _ = noise_tape((N, C, T), 1000, seed=99)
+    x50, tape50 = noise_tape((N, C, T), 50, seed=5)
+    seed_len = params.Generate.pose_seed_len
+    seedp = th.randn(N, T, C, generator=th.Generator().manual_seed(17))
+    masks = th.ones(N, T, 1)
+    masks[:, seed_len:] = 0
+    cases = {
+        "boost.ddim50.final": dict(noise=x_T, sample_alg="ddim"),
+        "boost.ddpm50.final": dict(noise=x50, sample_alg="ddpm", noise_tape=tape50),
+        "boost.ddpm50_inpaint.final": dict(noise=x50, sample_alg="ddpm", noise_tape=tape50, inpaint_poses=seedp,
+                                           inpaint_masks=masks, trans_factor=0.575, pose_seed_len=seed_len),
+        "boost.ddim50_inpaint.final": dict(noise=x50, sample_alg="ddim", inpaint_poses=seedp, inpaint_masks=masks,
+                                           trans_factor=None, pose_seed_len=seed_len),
+    }
+    for key, kw in cases.items():
+        out = gen.generate_sample((N, C, T), wav, device="cuda", progress=False, **kw)
+        err = rel_l2(out, g[key])
+        print(f"[{name}] {key}: rel-L2 {err:.3e}")
+        assert err < 2e-2, f"{name} {key}: {err:.3e}"
+    # in-painted seed frames with trans_factor=None are copied exactly (f=0, m=1): x0 = seed at every step
+    out = gen.generate_sample((N, C, T), wav, device="cuda", progress=False, **cases["boost.ddim50_inpaint.final"])
+    assert rel_l2(out[:, :seed_len].cpu(), seedp[:, :seed_len]) < 1e-5
