@@ -14,8 +14,7 @@
 
 namespace gd {
 
-constexpr int ATT_THREADS = 128;
-constexpr int ATT_WARPS = ATT_THREADS / 32;
+constexpr int ATT_MAX_WARPS = 12;  // warps per CTA are chosen per launch: one 16-query tile per warp when possible
 constexpr int SEG = 8;  // tokens per conv work item
 
 struct AttnParams {
@@ -70,7 +69,7 @@ __device__ __forceinline__ void conv_stage(__nv_bfloat16* dst, int L, int L_pad,
     constexpr int STR = DK + 8;
     constexpr int CH = DK / 8;
     const int n_seg = (L_pad + SEG - 1) / SEG;
-    for (int item = threadIdx.x; item < n_seg * CH; item += ATT_THREADS) {
+    for (int item = threadIdx.x; item < n_seg * CH; item += blockDim.x) {
         const int ch = item % CH, sg = item / CH;
         const int c0 = ch * 8, p0 = sg * SEG;
         float w0[8], w1[8], w2[8], bb[8];
@@ -129,7 +128,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
 
 // KB = number of 16-key blocks (keys padded to 16*KB), DK = head width
 template <typename T, int DK, int KB>
-__global__ void __launch_bounds__(ATT_THREADS) dconv_attention_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(ATT_MAX_WARPS * 32) dconv_attention_kernel(const AttnParams p) {
     constexpr int STR = DK + 8;  // bf16 elements per smem row: +16 B keeps ldmatrix rows on distinct banks
     constexpr int LK_PAD = KB * 16;
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -140,7 +139,7 @@ __global__ void __launch_bounds__(ATT_THREADS) dconv_attention_kernel(const Attn
     float* s_taps = reinterpret_cast<float*>(sv + LK_PAD * STR);  // [3][DK*3 + DK]
     const int clip = blockIdx.x / p.heads, head = blockIdx.x % p.heads;
 
-    for (int i = threadIdx.x; i < 3 * DK * 4; i += ATT_THREADS) {
+    for (int i = threadIdx.x; i < 3 * DK * 4; i += blockDim.x) {
         const int which = i / (DK * 4), j = i % (DK * 4);
         const float* w = which == 0 ? p.wq : (which == 1 ? p.wk : p.wv);
         const float* b = which == 0 ? p.bq : (which == 1 ? p.bk : p.bv);
@@ -156,7 +155,8 @@ __global__ void __launch_bounds__(ATT_THREADS) dconv_attention_kernel(const Attn
     const int g = lane >> 2, t = lane & 3;
     const uint32_t sq_u = smem_u32(sq), sk_u = smem_u32(sk), sv_u = smem_u32(sv);
 
-    for (int qt = warp; qt * 16 < p.Lq; qt += ATT_WARPS) {
+    const int n_warps = blockDim.x >> 5;
+    for (int qt = warp; qt * 16 < p.Lq; qt += n_warps) {
         // ---- S = Q Kᵀ : 16 x LK_PAD, fp32 accumulators in registers
         float s[KB * 2][4];
 #pragma unroll
@@ -242,13 +242,25 @@ template <typename T, int DK, int KB>
 static int launch_attention(const AttnParams& p, int n_clips, cudaStream_t s) {
     const int Lq_pad = (p.Lq + 15) & ~15;
     const size_t smem = (size_t)(Lq_pad + 2 * KB * 16) * (DK + 8) * 2 + 3 * DK * 4 * sizeof(float);
-    static size_t configured = 48 * 1024;
+    static size_t configured = 0;
     if (smem > configured) {
+        const size_t want = smem > 48 * 1024 ? smem : 48 * 1024;
         GD_CUDA_CHECK(cudaFuncSetAttribute(dconv_attention_kernel<T, DK, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)smem));
-        configured = smem;
+                                           (int)want));
+        // without this the driver sizes the L1/smem split for ONE block and occupancy collapses to 1 CTA/SM
+        GD_CUDA_CHECK(cudaFuncSetAttribute(dconv_attention_kernel<T, DK, KB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                           cudaSharedmemCarveoutMaxShared));
+        configured = want;
     }
-    dconv_attention_kernel<T, DK, KB><<<n_clips * p.heads, ATT_THREADS, smem, s>>>(p);
+    // 4-5 warps per CTA and several CTAs per SM hide latency better than one fat CTA (measured); pick the count that
+    // leaves the fewest idle warp-rounds over the 16-query tiles
+    const int tiles = Lq_pad / 16;
+    int warps = 4;
+    if (tiles > 4) {
+        const int r4 = (tiles + 3) / 4, r5 = (tiles + 4) / 5;
+        warps = (r5 * 5 - tiles < r4 * 4 - tiles) ? 5 : 4;
+    }
+    dconv_attention_kernel<T, DK, KB><<<n_clips * p.heads, warps * 32, smem, s>>>(p);
     count_launch();
     GD_CUDA_CHECK(cudaGetLastError());
     return GD_OK;

@@ -3,10 +3,15 @@
 //   warp 0      TMA producer   (cp.async.bulk.tensor 2-D, SWIZZLE_128B tiles, mbarrier ring)
 //   warp 1      MMA issuer     (one thread: tcgen05.mma cta_group::1 kind::f16, 128 x BN x 16)
 //   warp 2      TMEM allocator (512 columns = two BN-wide fp32 accumulator stages for BN <= 256)
-//   warps 4..7  epilogue       (tcgen05.ld 32x32b -> registers -> bias/PE/activation/residual -> HBM)
+//   warps 4..11 epilogue       (tcgen05.ld 32x32b -> registers -> bias/activation -> swizzled smem -> TMA store)
 //
 // The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile
-// i+1; K is short on this workload (128..2048), so that overlap is where the time is.
+// i+1; K is short on this workload (128..2048), so that overlap is where the time is.  Eight epilogue warps
+// (two per scheduler; warp w owns TMEM lane quadrant w%4 and column half w/4) write 32x32 chunks into a
+// 128B/64B-swizzled staging tile and hand them to the TMA engine: plain tensor stores for bf16 outputs, and
+// `cp.reduce.async.bulk.tensor ... add.f32` for the in-place residual GEMMs (H += A·Wᵀ + b), so the residual is
+// added inside L2 and the SMs never load it.  Odd cases (positional rowbias, out-of-place residual, dual
+// outputs) take the simple per-row path (MODE_DIRECT).
 // MODE_DDPM turns the epilogue of the final projection into the DDPM ancestral update
 // (gd_b200.h: gd_linear_ddpm): eps stays in registers.
 #include "common.cuh"
@@ -18,9 +23,12 @@ namespace gd {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
-constexpr int MODE_STORE = 0;
-constexpr int MODE_DDPM = 1;
+constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps
+constexpr int EPI_WARPS = 8;
+constexpr int MODE_DIRECT = 0;    // per-row stores straight from registers (any epilogue feature)
+constexpr int MODE_DDPM = 1;      // final projection + DDPM update
+constexpr int MODE_TMA_BF16 = 2;  // bf16 output through TMA stores
+constexpr int MODE_TMA_F32 = 3;   // fp32 output through TMA stores, or TMA reduce-add when accumulating in place
 
 struct GemmParams {
     int M, N, K;
@@ -34,6 +42,7 @@ struct GemmParams {
     int ldo_f32;
     __nv_bfloat16* out_bf16;
     int ldo_bf16;
+    int reduce_add;  // MODE_TMA_F32: 1 = out += result (in-place residual), 0 = out = result
     gd_ddpm_desc ddpm;
 };
 
@@ -43,7 +52,8 @@ struct GemmCfg {
     static constexpr int B_BYTES = BN * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int STAGING_BYTES = EPI_WARPS * 32 * 32 * 4;  // per epilogue warp: 32 rows x 32 fp32 columns
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*barriers*/ + STAGING_BYTES + 1024 /*align slack*/;
     static constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
 };
 
@@ -56,8 +66,18 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
-// Epilogue for one thread = one output row, 32 consecutive columns starting at col0.
-__device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, int row, int col0, uint32_t (&v)[32]) {
+__device__ __forceinline__ void add_bias_chunk(float (&r)[32], const uint32_t (&v)[32], const float4 (&b)[8], bool has_bias) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        r[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + (has_bias ? b[j].x : 0.f);
+        r[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + (has_bias ? b[j].y : 0.f);
+        r[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + (has_bias ? b[j].z : 0.f);
+        r[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + (has_bias ? b[j].w : 0.f);
+    }
+}
+
+// MODE_DIRECT: one thread = one output row, 32 consecutive columns starting at col0, every epilogue feature.
+__device__ __forceinline__ void epilogue_direct_chunk(const GemmParams& p, int row, int col0, uint32_t (&v)[32]) {
     float r[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]);
@@ -66,10 +86,7 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, int ro
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float4 b = __ldg(b4 + j);
-            r[4 * j + 0] += b.x;
-            r[4 * j + 1] += b.y;
-            r[4 * j + 2] += b.z;
-            r[4 * j + 3] += b.w;
+            r[4 * j + 0] += b.x, r[4 * j + 1] += b.y, r[4 * j + 2] += b.z, r[4 * j + 3] += b.w;
         }
     }
     if (p.rowbias) {
@@ -78,10 +95,7 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, int ro
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float4 b = __ldg(b4 + j);
-            r[4 * j + 0] += b.x;
-            r[4 * j + 1] += b.y;
-            r[4 * j + 2] += b.z;
-            r[4 * j + 3] += b.w;
+            r[4 * j + 0] += b.x, r[4 * j + 1] += b.y, r[4 * j + 2] += b.z, r[4 * j + 3] += b.w;
         }
     }
     if (p.act != GD_ACT_NONE) {
@@ -93,10 +107,7 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, int ro
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float4 q = q4[j];
-            r[4 * j + 0] += q.x;
-            r[4 * j + 1] += q.y;
-            r[4 * j + 2] += q.z;
-            r[4 * j + 3] += q.w;
+            r[4 * j + 0] += q.x, r[4 * j + 1] += q.y, r[4 * j + 2] += q.z, r[4 * j + 3] += q.w;
         }
     }
     if (p.out_f32) {
@@ -169,19 +180,20 @@ __device__ __forceinline__ void epilogue_ddpm_chunk(const GemmParams& p, const D
 template <int BN, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
     using Cfg = GemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);  // 256 B reserved
     uint64_t* full_bar = bars;                    // [STAGES]  TMA -> MMA
     uint64_t* empty_bar = bars + STAGES;          // [STAGES]  MMA -> TMA
     uint64_t* acc_full_bar = bars + 2 * STAGES;   // [2]       MMA -> epilogue
     uint64_t* acc_empty_bar = acc_full_bar + 2;   // [2]       epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty_bar + 2);
+    uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES + 1024;  // 1024-B aligned: TMA swizzle atoms
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -193,6 +205,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&tmap_a);
         prefetch_tensormap(&tmap_b);
+        if (MODE == MODE_TMA_BF16 || MODE == MODE_TMA_F32) prefetch_tensormap(&tmap_out);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -201,7 +214,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&acc_full_bar[s], 1);
-            mbar_init(&acc_empty_bar[s], 4);  // one arrive per epilogue warp
+            mbar_init(&acc_empty_bar[s], EPI_WARPS);  // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -262,13 +275,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
         }
     } else if (warp >= 4) {
-        const int ew = warp - 4;  // TMEM lanes [32*ew, 32*ew+32)
+        const int ew = warp - 4;
+        const int quad = ew & 3;    // TMEM lanes [32*quad, 32*quad+32)  (a warp may only touch quadrant warp%4)
+        const int half = ew >> 2;   // which half of the tile's columns
+        constexpr int WCOLS = BN / 2;
         int t = 0;
         DdpmStepCoefs cf;
         if (MODE == MODE_DDPM) {
             t = *p.ddpm.step_ptr;
             cf = ddpm_load_coefs(p.ddpm, t);
         }
+        uint8_t* stg = staging + ew * 4096;
+        const bool has_bias = p.bias != nullptr;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int m0 = (tile / n_tiles) * BLOCK_M;
@@ -277,24 +295,79 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&acc_full_bar[acc], acc_phase);
             tc_fence_after_sync();
-            const int row = m0 + ew * 32 + lane;
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+            const int row0 = m0 + quad * 32;
+            const int row = row0 + lane;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * WCOLS;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = 0; c < WCOLS / 32; ++c) {
+                const int col0 = n0 + half * WCOLS + c * 32;
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(taddr + c * 32, v);
-                tmem_ld_wait();
-                if (row < p.M) {
-                    if (MODE == MODE_DDPM)
-                        epilogue_ddpm_chunk(p, cf, t, row, n0 + c * 32, v);
-                    else
-                        epilogue_store_chunk(p, row, n0 + c * 32, v);
+                if (MODE == MODE_TMA_BF16 || MODE == MODE_TMA_F32) {
+                    // bias loads are issued while the TMEM load is in flight
+                    float4 b[8];
+                    if (has_bias) {
+                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) b[j] = __ldg(b4 + j);
+                    }
+                    tmem_ld_wait();
+                    float r[32];
+                    add_bias_chunk(r, v, b, has_bias);
+                    if (p.act == GD_ACT_RELU2) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float m = fmaxf(r[j], 0.f);
+                            r[j] = m * m;
+                        }
+                    } else if (p.act == GD_ACT_SILU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] = apply_act(r[j], GD_ACT_SILU);
+                    }
+                    // the previous TMA store of this warp must have finished READING the staging tile
+                    if (lane == 0) bulk_wait_group_read0();
+                    __syncwarp();
+                    if (MODE == MODE_TMA_F32) {
+                        float4* st4 = reinterpret_cast<float4*>(stg);  // 128-B rows, SWIZZLE_128B: chunk ^= row & 7
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            st4[lane * 8 + (j ^ (lane & 7))] = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                    } else {
+                        uint4* st4 = reinterpret_cast<uint4*>(stg);  // 64-B rows, SWIZZLE_64B: chunk ^= (row >> 1) & 3
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 w;
+                            w.x = pack_bf16x2(r[8 * j + 0], r[8 * j + 1]);
+                            w.y = pack_bf16x2(r[8 * j + 2], r[8 * j + 3]);
+                            w.z = pack_bf16x2(r[8 * j + 4], r[8 * j + 5]);
+                            w.w = pack_bf16x2(r[8 * j + 6], r[8 * j + 7]);
+                            st4[lane * 4 + (j ^ ((lane >> 1) & 3))] = w;
+                        }
+                    }
+                    fence_proxy_async();  // make the generic-proxy smem writes visible to the TMA engine
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (MODE == MODE_TMA_F32 && p.reduce_add)
+                            tma_reduce_add_2d(&tmap_out, stg, col0, row0);
+                        else
+                            tma_store_2d(&tmap_out, stg, col0, row0);
+                        bulk_commit_group();
+                    }
+                } else {
+                    tmem_ld_wait();
+                    if (row < p.M) {
+                        if (MODE == MODE_DDPM)
+                            epilogue_ddpm_chunk(p, cf, t, row, col0, v);
+                        else
+                            epilogue_direct_chunk(p, row, col0, v);
+                    }
                 }
             }
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty_bar[acc]);
         }
+        if ((MODE == MODE_TMA_BF16 || MODE == MODE_TMA_F32) && lane == 0) bulk_wait_group0();
     }
 
     tc_fence_before_sync();
@@ -303,28 +376,40 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------ host
-static int make_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
-                             uint32_t box_rows) {
+static int make_tmap_2d(CUtensorMap* m, CUtensorMapDataType dt, int elt_bytes, const void* base, uint64_t rows,
+                        uint64_t cols, uint64_t ld_elems, uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swz) {
     static PFN_encodeTiled encode = get_encode_tiled();
     if (!encode) return set_error(GD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {ld_elems * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, box_rows};
+    cuuint64_t strides[1] = {ld_elems * elt_bytes};
+    cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = encode(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(GD_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
     return GD_OK;
+}
+static int make_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                             uint32_t box_rows) {
+    return make_tmap_2d(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, cols, ld_elems, BLOCK_K, box_rows,
+                        CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 template <int BN, int MODE>
 static int launch_gemm(const GemmParams& p, const void* A, int lda, const void* W, int ldw, cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, tout;
     int rc = make_tmap_2d_bf16(&ta, A, p.M, p.K, lda, BLOCK_M);
     if (rc) return rc;
     rc = make_tmap_2d_bf16(&tb, W, p.N, p.K, ldw, BN);
+    if (rc) return rc;
+    tout = ta;  // unused unless a TMA epilogue is selected
+    if (MODE == MODE_TMA_BF16)
+        rc = make_tmap_2d(&tout, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.out_bf16, p.M, p.N, p.ldo_bf16, 32, 32,
+                          CU_TENSOR_MAP_SWIZZLE_64B);
+    else if (MODE == MODE_TMA_F32)
+        rc = make_tmap_2d(&tout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.out_f32, p.M, p.N, p.ldo_f32, 32, 32,
+                          CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
@@ -335,7 +420,7 @@ static int launch_gemm(const GemmParams& p, const void* A, int lda, const void* 
     const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
     const int tiles = m_tiles * (p.N / BN);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    gemm_bf16_tn_kernel<BN, MODE><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+    gemm_bf16_tn_kernel<BN, MODE><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tout, p);
     count_launch();
     GD_CUDA_CHECK(cudaGetLastError());
     return GD_OK;
@@ -375,12 +460,29 @@ extern "C" int gd_linear_bf16(const gd_linear_desc* d, void* stream) {
     p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(d->out_bf16), p.ldo_bf16 = d->ldo_bf16;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const int m_tiles = (d->M + BLOCK_M - 1) / BLOCK_M;
+    // epilogue flavour: TMA stores for the two hot shapes, the per-row path for everything else
+    int mode = MODE_DIRECT;
+    const bool aligned16 = ((reinterpret_cast<uintptr_t>(d->out_f32) | reinterpret_cast<uintptr_t>(d->out_bf16)) & 15) == 0;
+    if (!d->rowbias && aligned16) {
+        if (d->out_bf16 && !d->out_f32 && !d->residual)
+            mode = MODE_TMA_BF16;
+        else if (d->out_f32 && !d->out_bf16 && (!d->residual || (d->residual == d->out_f32 && d->ldr == d->ldo_f32))) {
+            mode = MODE_TMA_F32;
+            p.reduce_add = d->residual != nullptr;
+            p.residual = nullptr;
+        }
+    }
     // Widest tile that still gives every SM work; narrow tiles when the problem is small.
-    if (d->N % 256 == 0 && m_tiles * (d->N / 256) >= sm_count())
-        return launch_gemm<256, MODE_STORE>(p, d->A, d->lda, d->W, d->ldw, s);
-    if (d->N % 128 == 0 && m_tiles * (d->N / 128) >= sm_count())
-        return launch_gemm<128, MODE_STORE>(p, d->A, d->lda, d->W, d->ldw, s);
-    return launch_gemm<64, MODE_STORE>(p, d->A, d->lda, d->W, d->ldw, s);
+    const int bn = (d->N % 256 == 0 && m_tiles * (d->N / 256) >= sm_count()) ? 256
+                   : (d->N % 128 == 0 && m_tiles * (d->N / 128) >= sm_count()) ? 128 : 64;
+#define GD_LAUNCH(BN_)                                                                                   \
+    (mode == MODE_TMA_BF16  ? launch_gemm<BN_, MODE_TMA_BF16>(p, d->A, d->lda, d->W, d->ldw, s)          \
+     : mode == MODE_TMA_F32 ? launch_gemm<BN_, MODE_TMA_F32>(p, d->A, d->lda, d->W, d->ldw, s)           \
+                            : launch_gemm<BN_, MODE_DIRECT>(p, d->A, d->lda, d->W, d->ldw, s))
+    if (bn == 256) return GD_LAUNCH(256);
+    if (bn == 128) return GD_LAUNCH(128);
+    return GD_LAUNCH(64);
+#undef GD_LAUNCH
 }
 
 extern "C" int gd_linear_ddpm(const gd_linear_desc* d, const gd_ddpm_desc* u, void* stream) {

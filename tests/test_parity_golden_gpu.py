@@ -50,7 +50,7 @@ def test_full_chain_vs_reference(name, precision):
         x_T, tape = noise_tape((N, C, T), 1000, seed=99)
         out = Generator(model, diffusion).generate_sample((N, C, T), wav, noise=x_T, sample_alg="ddpm", device="cuda",
                                                           progress=False, noise_tape=tape)
-        err = rel_l2(out, g[f"{weights}.ddpm.final"])
+        err = rel_l2(out.transpose(1, 2), g[f"{weights}.ddpm.final"])
         print(f"[{name}/{weights}/{precision}] final pose rel-L2 vs reference: {err:.3e}")
         assert err < POSE_TOL[precision], f"{name}/{weights}/{precision}: final pose rel-L2 {err:.3e}"
 
