@@ -14,8 +14,7 @@
 
 namespace gd {
 
-constexpr int ATT_MAX_WARPS = 12;  // warps per CTA are chosen per launch: one 16-query tile per warp when possible
-constexpr int SEG = 8;  // tokens per conv work item
+constexpr int ATT_MAX_WARPS = 5;  // 4 or 5 warps per CTA (chosen per launch), several CTAs per SM
 
 struct AttnParams {
     const void* q[2];
@@ -28,50 +27,67 @@ struct AttnParams {
     float scale_log2;  // d_k^-1/2 * log2(e)
 };
 
-// 8 consecutive elements of a projected row as fp32
+// Raw (pre-conv) storage of 8 consecutive elements of a projected row: one 16-B load for bf16, two for fp32.
+// Loads go through the non-coherent path (ld.global.nc) so the compiler may batch them ahead of the smem stores.
 template <typename T>
-__device__ __forceinline__ void load8(const T* p, float (&f)[8]);
+struct Raw8;
 template <>
-__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
-    const uint4 u = *reinterpret_cast<const uint4*>(p);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+struct Raw8<__nv_bfloat16> {
+    uint4 u;
+    __device__ __forceinline__ void load(const __nv_bfloat16* p) { u = __ldg(reinterpret_cast<const uint4*>(p)); }
+    __device__ __forceinline__ void zero() { u = make_uint4(0, 0, 0, 0); }
+    __device__ __forceinline__ void unpack(float (&f)[8]) const {
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        f[2 * i] = __uint_as_float(w[i] << 16);
-        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        for (int i = 0; i < 4; ++i) {
+            f[2 * i] = __uint_as_float(w[i] << 16);
+            f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
     }
-}
+};
 template <>
-__device__ __forceinline__ void load8<float>(const float* p, float (&f)[8]) {
-    const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
-    f[0] = a.x, f[1] = a.y, f[2] = a.z, f[3] = a.w, f[4] = b.x, f[5] = b.y, f[6] = b.z, f[7] = b.w;
-}
+struct Raw8<float> {
+    float4 a, b;
+    __device__ __forceinline__ void load(const float* p) {
+        a = __ldg(reinterpret_cast<const float4*>(p));
+        b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    }
+    __device__ __forceinline__ void zero() { a = b = make_float4(0.f, 0.f, 0.f, 0.f); }
+    __device__ __forceinline__ void unpack(float (&f)[8]) const {
+        f[0] = a.x, f[1] = a.y, f[2] = a.z, f[3] = a.w, f[4] = b.x, f[5] = b.y, f[6] = b.z, f[7] = b.w;
+    }
+};
 
 template <typename T>
-__device__ __forceinline__ void raw_row8(const void* const (&seg)[2], const int (&rows)[2], const int (&ld)[2], int clip,
-                                         int pos, int L, int col, float (&f)[8]) {
+__device__ __forceinline__ void raw_row8(Raw8<T>& r, const void* const (&seg)[2], const int (&rows)[2], const int (&ld)[2],
+                                         int clip, int pos, int L, int col) {
     if (pos < 0 || pos >= L) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = 0.f;
+        r.zero();
         return;
     }
     const T* p = (pos < rows[0])
                      ? reinterpret_cast<const T*>(seg[0]) + ((size_t)clip * rows[0] + pos) * ld[0] + col
                      : reinterpret_cast<const T*>(seg[1]) + ((size_t)clip * rows[1] + (pos - rows[0])) * ld[1] + col;
-    load8<T>(p, f);
+    r.load(p);
 }
 
-// dst[pos][c] = bf16( w[c][0]*raw[pos-1][c] + w[c][1]*raw[pos][c] + w[c][2]*raw[pos+1][c] + b[c] ), rows >= L zeroed
+// dst[pos][c] = bf16( w[c][0]*raw[pos-1][c] + w[c][1]*raw[pos][c] + w[c][2]*raw[pos+1][c] + b[c] ), rows >= L zeroed.
+// One work item = SEGT consecutive tokens x 8 columns: all SEGT+2 raw rows are fetched up front (SEGT+2 independent
+// 16-B loads in flight per thread), then the 3-tap FIR slides over them in registers.
 template <typename T, int DK>
 __device__ __forceinline__ void conv_stage(__nv_bfloat16* dst, int L, int L_pad, const void* const (&seg)[2],
                                            const int (&rows)[2], const int (&ld)[2], int clip, int head,
                                            const float* s_taps /* [DK*3] */, const float* s_bias /* [DK] */) {
     constexpr int STR = DK + 8;
     constexpr int CH = DK / 8;
-    const int n_seg = (L_pad + SEG - 1) / SEG;
+    constexpr int SEGT = sizeof(T) == 2 ? 8 : 4;
+    const int n_seg = (L_pad + SEGT - 1) / SEGT;
     for (int item = threadIdx.x; item < n_seg * CH; item += blockDim.x) {
         const int ch = item % CH, sg = item / CH;
-        const int c0 = ch * 8, p0 = sg * SEG;
+        const int c0 = ch * 8, p0 = sg * SEGT;
+        Raw8<T> raw[SEGT + 2];
+#pragma unroll
+        for (int s = 0; s < SEGT + 2; ++s) raw_row8<T>(raw[s], seg, rows, ld, clip, p0 - 1 + s, L, head * DK + c0);
         float w0[8], w1[8], w2[8], bb[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -81,24 +97,25 @@ __device__ __forceinline__ void conv_stage(__nv_bfloat16* dst, int L, int L_pad,
             bb[i] = s_bias[c0 + i];
         }
         float prev[8], cur[8], nxt[8];
-        raw_row8<T>(seg, rows, ld, clip, p0 - 1, L, head * DK + c0, prev);
-        raw_row8<T>(seg, rows, ld, clip, p0, L, head * DK + c0, cur);
+        raw[0].unpack(prev);
+        raw[1].unpack(cur);
 #pragma unroll
-        for (int s = 0; s < SEG; ++s) {
+        for (int s = 0; s < SEGT; ++s) {
             const int pos = p0 + s;
-            if (pos >= L_pad) break;
-            raw_row8<T>(seg, rows, ld, clip, pos + 1, L, head * DK + c0, nxt);
-            uint4 o = make_uint4(0, 0, 0, 0);
-            if (pos < L) {
-                float r[8];
+            raw[s + 2].unpack(nxt);
+            if (pos < L_pad) {
+                uint4 o = make_uint4(0, 0, 0, 0);
+                if (pos < L) {
+                    float r[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) r[i] = w0[i] * prev[i] + w1[i] * cur[i] + w2[i] * nxt[i] + bb[i];
-                o.x = pack_bf16x2(r[0], r[1]);
-                o.y = pack_bf16x2(r[2], r[3]);
-                o.z = pack_bf16x2(r[4], r[5]);
-                o.w = pack_bf16x2(r[6], r[7]);
+                    for (int i = 0; i < 8; ++i) r[i] = w0[i] * prev[i] + w1[i] * cur[i] + w2[i] * nxt[i] + bb[i];
+                    o.x = pack_bf16x2(r[0], r[1]);
+                    o.y = pack_bf16x2(r[2], r[3]);
+                    o.z = pack_bf16x2(r[4], r[5]);
+                    o.w = pack_bf16x2(r[6], r[7]);
+                }
+                *reinterpret_cast<uint4*>(dst + pos * STR + c0) = o;
             }
-            *reinterpret_cast<uint4*>(dst + pos * STR + c0) = o;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 prev[i] = cur[i];
@@ -128,7 +145,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
 
 // KB = number of 16-key blocks (keys padded to 16*KB), DK = head width
 template <typename T, int DK, int KB>
-__global__ void __launch_bounds__(ATT_MAX_WARPS * 32) dconv_attention_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(ATT_MAX_WARPS * 32, 3) dconv_attention_kernel(const AttnParams p) {
     constexpr int STR = DK + 8;  // bf16 elements per smem row: +16 B keeps ldmatrix rows on distinct banks
     constexpr int LK_PAD = KB * 16;
     extern __shared__ __align__(16) uint8_t smem_raw[];
