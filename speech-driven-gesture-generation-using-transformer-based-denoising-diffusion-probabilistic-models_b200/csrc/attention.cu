@@ -58,22 +58,22 @@ struct Raw8<float> {
     }
 };
 
+// Branch-free fetch of 8 elements of token `pos` of the concatenated per-clip sequence (zeros outside [0, L)):
+// the address is formed from a clamped position with 32-bit offsets and selects, the result is masked.
 template <typename T>
-__device__ __forceinline__ void raw_row8(Raw8<T>& r, const void* const (&seg)[2], const int (&rows)[2], const int (&ld)[2],
-                                         int clip, int pos, int L, int col) {
-    if (pos < 0 || pos >= L) {
-        r.zero();
-        return;
-    }
-    const T* p = (pos < rows[0])
-                     ? reinterpret_cast<const T*>(seg[0]) + ((size_t)clip * rows[0] + pos) * ld[0] + col
-                     : reinterpret_cast<const T*>(seg[1]) + ((size_t)clip * rows[1] + (pos - rows[0])) * ld[1] + col;
+__device__ __forceinline__ void raw_row8(Raw8<T>& r, const T* base0, const T* base1, int rows0, int ld0, int ld1, int pos,
+                                         int L) {
+    const bool valid = static_cast<unsigned>(pos) < static_cast<unsigned>(L);
+    const int pc = min(max(pos, 0), L - 1);
+    const bool in0 = pc < rows0;
+    const T* p = in0 ? base0 + pc * ld0 : base1 + (pc - rows0) * ld1;
     r.load(p);
+    if (!valid) r.zero();
 }
 
 // dst[pos][c] = bf16( w[c][0]*raw[pos-1][c] + w[c][1]*raw[pos][c] + w[c][2]*raw[pos+1][c] + b[c] ), rows >= L zeroed.
 // One work item = SEGT consecutive tokens x 8 columns: all SEGT+2 raw rows are fetched up front (SEGT+2 independent
-// 16-B loads in flight per thread), then the 3-tap FIR slides over them in registers.
+// 16-B loads in flight per thread), then the 3-tap FIR slides over them in registers (3 FFMA per element).
 template <typename T, int DK>
 __device__ __forceinline__ void conv_stage(__nv_bfloat16* dst, int L, int L_pad, const void* const (&seg)[2],
                                            const int (&rows)[2], const int (&ld)[2], int clip, int head,
@@ -82,12 +82,15 @@ __device__ __forceinline__ void conv_stage(__nv_bfloat16* dst, int L, int L_pad,
     constexpr int CH = DK / 8;
     constexpr int SEGT = sizeof(T) == 2 ? 8 : 4;
     const int n_seg = (L_pad + SEGT - 1) / SEGT;
+    const int rows0 = rows[0], ld0 = ld[0], ld1 = ld[1];
+    const T* clip0 = reinterpret_cast<const T*>(seg[0]) + (size_t)clip * rows0 * ld0 + head * DK;
+    const T* clip1 = seg[1] ? reinterpret_cast<const T*>(seg[1]) + (size_t)clip * rows[1] * ld1 + head * DK : clip0;
     for (int item = threadIdx.x; item < n_seg * CH; item += blockDim.x) {
         const int ch = item % CH, sg = item / CH;
         const int c0 = ch * 8, p0 = sg * SEGT;
         Raw8<T> raw[SEGT + 2];
 #pragma unroll
-        for (int s = 0; s < SEGT + 2; ++s) raw_row8<T>(raw[s], seg, rows, ld, clip, p0 - 1 + s, L, head * DK + c0);
+        for (int s = 0; s < SEGT + 2; ++s) raw_row8<T>(raw[s], clip0 + c0, clip1 + c0, rows0, ld0, ld1, p0 - 1 + s, L);
         float w0[8], w1[8], w2[8], bb[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -103,19 +106,16 @@ __device__ __forceinline__ void conv_stage(__nv_bfloat16* dst, int L, int L_pad,
         for (int s = 0; s < SEGT; ++s) {
             const int pos = p0 + s;
             raw[s + 2].unpack(nxt);
-            if (pos < L_pad) {
-                uint4 o = make_uint4(0, 0, 0, 0);
-                if (pos < L) {
-                    float r[8];
+            float r[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) r[i] = w0[i] * prev[i] + w1[i] * cur[i] + w2[i] * nxt[i] + bb[i];
-                    o.x = pack_bf16x2(r[0], r[1]);
-                    o.y = pack_bf16x2(r[2], r[3]);
-                    o.z = pack_bf16x2(r[4], r[5]);
-                    o.w = pack_bf16x2(r[6], r[7]);
-                }
-                *reinterpret_cast<uint4*>(dst + pos * STR + c0) = o;
-            }
+            for (int i = 0; i < 8; ++i) r[i] = fmaf(w0[i], prev[i], fmaf(w1[i], cur[i], fmaf(w2[i], nxt[i], bb[i])));
+            uint4 o;
+            o.x = pack_bf16x2(r[0], r[1]);
+            o.y = pack_bf16x2(r[2], r[3]);
+            o.z = pack_bf16x2(r[4], r[5]);
+            o.w = pack_bf16x2(r[6], r[7]);
+            if (pos >= L) o = make_uint4(0, 0, 0, 0);
+            if (pos < L_pad) *reinterpret_cast<uint4*>(dst + pos * STR + c0) = o;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 prev[i] = cur[i];
@@ -125,6 +125,11 @@ __device__ __forceinline__ void conv_stage(__nv_bfloat16* dst, int L, int L_pad,
     }
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {  // MUFU.EX2; -inf -> 0, which is what masked keys need
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
                  : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
@@ -191,13 +196,15 @@ __global__ void __launch_bounds__(ATT_MAX_WARPS * 32, 3) dconv_attention_kernel(
                 mma_bf16_16816(s[2 * nb + 1], a0, a1, a2, a3, b2, b3);
             }
         }
-        // ---- softmax over keys (rows g and g+8 of the tile), padded keys masked
+        // ---- softmax over keys (rows g and g+8 of the tile); only the last key tiles can hold padded keys
         float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
         for (int n = 0; n < KB * 2; ++n) {
-            const int j = n * 8 + 2 * t;
-            if (j >= p.Lk) s[n][0] = s[n][2] = -INFINITY;
-            if (j + 1 >= p.Lk) s[n][1] = s[n][3] = -INFINITY;
+            if (n >= KB * 2 - 2 && n * 8 + 8 > p.Lk) {  // warp-uniform; at most the two tiles of the last 16-key block
+                const int j = n * 8 + 2 * t;
+                if (j >= p.Lk) s[n][0] = s[n][2] = -INFINITY;
+                if (j + 1 >= p.Lk) s[n][1] = s[n][3] = -INFINITY;
+            }
             m0 = fmaxf(m0, fmaxf(s[n][0], s[n][1]));
             m1 = fmaxf(m1, fmaxf(s[n][2], s[n][3]));
         }
@@ -209,10 +216,10 @@ __global__ void __launch_bounds__(ATT_MAX_WARPS * 32, 3) dconv_attention_kernel(
         float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
         for (int n = 0; n < KB * 2; ++n) {
-            s[n][0] = exp2f(s[n][0] * p.scale_log2 - o0);
-            s[n][1] = exp2f(s[n][1] * p.scale_log2 - o0);
-            s[n][2] = exp2f(s[n][2] * p.scale_log2 - o1);
-            s[n][3] = exp2f(s[n][3] * p.scale_log2 - o1);
+            s[n][0] = ex2_approx(fmaf(s[n][0], p.scale_log2, -o0));
+            s[n][1] = ex2_approx(fmaf(s[n][1], p.scale_log2, -o0));
+            s[n][2] = ex2_approx(fmaf(s[n][2], p.scale_log2, -o1));
+            s[n][3] = ex2_approx(fmaf(s[n][3], p.scale_log2, -o1));
             sum0 += s[n][0] + s[n][1];
             sum1 += s[n][2] + s[n][3];
         }

@@ -101,10 +101,12 @@ class PackedWeights:
 
 class Op:
     """One kernel launch of the step plan, with the algorithmic work it performs (bench.py's roofline inputs)."""
-    __slots__ = ("fn", "kind", "flops", "bytes")
+    __slots__ = ("fn", "kind", "flops", "bytes", "group", "lane")
 
     def __init__(self, fn, kind, flops=0, nbytes=0):
         self.fn, self.kind, self.flops, self.bytes = fn, kind, flops, nbytes
+        # ops of one `group` > 0 form a concurrent region: lane 0 runs on the main stream, lane 1 on the side stream
+        self.group, self.lane = 0, 0
 
     def __call__(self):
         self.fn()
@@ -186,6 +188,8 @@ class SamplingChain:
         self.tape = None
         self.blend = None
         self.plan = None
+        self.side = th.cuda.Stream(device=device)
+        self.concurrent = getattr(model, "concurrent_streams", True)
         self.graph = None
         self._plan_key = None
         self.Tm = None
@@ -304,17 +308,30 @@ class SamplingChain:
             ao = th.empty(R, d, device=dev, dtype=th.bfloat16)
             hid = th.empty(R, 4 * d, device=dev, dtype=th.bfloat16)
             X, Mem = H[:Mx], H[Mx:]
+            # The pose stream and the memory stream only meet in the joint attention, so [FFN(l-1), self-attn(l)] of the
+            # two streams are tagged as concurrent regions: small pose-stream kernels fill the tails of the memory-stream ones.
+            def tag(start, group, lane):
+                for op in ops[start:]:
+                    op.group, op.lane = group, lane
+            region = 1
             a_sc = (_p(Mem), _p(cond["mem_init"]), _p(cond["mem_tab"]), _p(self.step), N, Tm, 0, d, d)
             ops.append(Op(lambda: gd.check(lib.gd_scatter_step_row_f32(*a_sc, L.stream()), "gd_scatter_step_row_f32"),
                           "scatter", 0, 8 * Mm * d))
+            tag(len(ops) - 1, region, 1)
             ops.append(L.linear(self.xa, W.embx_w, Mx, d, _POSE_PAD, bias=W.embx_b, rowbias=W.pe, period=T, offset=0,
                                 out_f32=X, k_alg=self.C))
+            tag(len(ops) - 1, region, 0)
             for li, ly in enumerate(W.layers):
                 last = li == W.n_layers - 1
+                s0 = len(ops)
                 ops.append(L.layernorm(X, ly["ln_sa"], xn[:Mx], Mx, d))
                 self._attn_block(ops, ly["sa"], 0, Mx, [(0, T)], xn, qkv, ao, H, heads)
+                tag(s0, region, 0)
+                s0 = len(ops)
                 ops.append(L.layernorm(Mem, ly["ln_sam"], xn[Mx:], Mm, d))
                 self._attn_block(ops, ly["sam"], Mx, R, [(Mx, Tm)], xn, qkv, ao, H, heads)
+                tag(s0, region, 1)
+                region += 1
                 # joint attention over [x ; memory] (nn.py:105-113); last layer only the pose rows are read afterwards
                 ops.append(L.layernorm(H, ly["ln_ca"], xn, R, d))
                 a = ly["ca"]
@@ -328,9 +345,13 @@ class SamplingChain:
                 ops.append(L.attention(N, heads, d // heads, qs, ks, vs, os_, a["taps"], self.f32act))
                 Ro = Mx if last else R
                 ops.append(L.linear(ao[:Ro], a["wo"], Ro, d, d, bias=a["bo"], residual=H[:Ro], out_f32=H[:Ro]))
+                s0 = len(ops)
                 self._ffn_block(ops, ly["ff"], ly["ln_ff"], 0, Mx, xn, hid, H)
                 if "ffm" in ly:
+                    tag(s0, region, 0)
+                    s0 = len(ops)
                     self._ffn_block(ops, ly["ffm"], ly["ln_ffm"], Mx, R, xn, hid, H)
+                    tag(s0, region, 1)
         else:
             X = th.empty(Mx, d, device=dev)
             H = X
@@ -428,8 +449,24 @@ class SamplingChain:
         self.step.fill_(self.n_steps - 1)
 
     def step_eager(self):
+        """Enqueue one denoise step.  Concurrent regions fork onto the side stream and join back (inside a capture this
+        becomes graph-level parallelism)."""
+        main = th.cuda.current_stream()
+        cur = 0
         for op in self.plan:
-            op()
+            if op.group != cur:
+                if cur > 0:
+                    main.wait_stream(self.side)
+                if op.group > 0 and self.concurrent:
+                    self.side.wait_stream(main)
+                cur = op.group if self.concurrent else 0
+            if cur > 0 and op.lane == 1:
+                with th.cuda.stream(self.side):
+                    op()
+            else:
+                op()
+        if cur > 0:
+            main.wait_stream(self.side)
 
     def set_state(self, x, i):
         """Teacher forcing: overwrite the sample and the loop index (parity harness)."""
