@@ -144,6 +144,17 @@ __device__ __forceinline__ void epilogue_ddpm_chunk(const GemmParams& p, const D
         m = __ldg(u.inpaint_mask + (size_t)clip * u.T + frame);
         f = __ldg(u.inpaint_factor + frame);
     }
+    // all loads of the chunk first (x may alias the stores below, so the compiler cannot hoist them itself)
+    float xv[32], zv[32], sv[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int c = col0 + j;
+        const size_t idx = clip_base + (size_t)c * u.T;
+        const bool ok = c < u.C;
+        xv[j] = ok ? u.x[idx] : 0.f;
+        zv[j] = (ok && u.noise_tape) ? __ldg(u.noise_tape + tape_base + idx) : 0.f;
+        sv[j] = (ok && inpaint) ? __ldg(u.inpaint_seed + ((size_t)clip * u.T + frame) * u.C + c) : 0.f;
+    }
     float xn[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -152,11 +163,8 @@ __device__ __forceinline__ void epilogue_ddpm_chunk(const GemmParams& p, const D
         if (c < u.C) {
             const size_t idx = clip_base + (size_t)c * u.T;
             const float eps = __uint_as_float(v[j]) + __ldg(p.bias + c);
-            const float x = u.x[idx];
-            const float z = u.noise_tape ? __ldg(u.noise_tape + tape_base + idx) : 0.0f;
-            const float seed = inpaint ? __ldg(u.inpaint_seed + ((size_t)clip * u.T + frame) * u.C + c) : 0.0f;
             float x0;
-            const float xnext = ddpm_update_elem(cf, x, eps, z, inpaint, seed, m, f, u.clip_x0, &x0);
+            const float xnext = ddpm_update_elem(cf, xv[j], eps, zv[j], inpaint, sv[j], m, f, u.clip_x0, &x0);
             u.x[idx] = xnext;
             if (u.eps_out) u.eps_out[idx] = eps;
             if (u.x0_out) u.x0_out[idx] = x0;
