@@ -105,8 +105,8 @@ class CpuReference:
         from gesture_b200.presets import preset
         from gesture_b200.synthetic import noise_tape, synthetic_wav
         from oracle import ddpm_oracle as orc
-        if threads:
-            th.set_num_threads(threads)
+        # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can
+        th.set_num_threads(threads or os.cpu_count() or 1)
         self.orc = orc
         self.params, self.C, self.T, L = preset(workload)
         th.manual_seed(0)
@@ -262,11 +262,10 @@ def run_b200(args):
         gen = Generator(model, diffusion)
 
         def one_e2e():
-            poses = gen.generate_sample(shape, wav_host, noise=x_host, sample_alg="ddpm", device=dev, progress=False,
-                                        return_dtype="cpu_tensor")
+            poses = gen.generate_sample(shape, wav_host, noise=x_host, sample_alg="ddpm", device=dev, progress=False)
             if world > 1:
-                dist.all_gather_into_tensor(gathered, poses.to(dev))
-            return poses
+                dist.all_gather_into_tensor(gathered, poses.contiguous())
+            return poses.cpu()  # device -> host read of this rank's result
         one_e2e()
         barrier()
         s0, s1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)

@@ -52,7 +52,7 @@ class Generator:
         kw = {"noise_tape": noise_tape} if sample_alg == "ddpm" else {}
         sample = sample_func(self.model, shape, noise=noise, denoise_fn=denoise_fn, model_kwargs={"wav": wavs},
                              device=device, progress=progress, **kw)["sample"].transpose(1, 2)  # -> (N,T,C)
-        return self.tensor2dtype(sample.clone(), return_dtype)
+        return self.tensor2dtype(sample.contiguous(), return_dtype)  # a copy: the chain's buffers are reused
 
     @th.no_grad()
     def generate_sequence(self, wav_seqs, wav_sr, pose_dim, pose_fps, pose_window_len, pose_seed_len,
