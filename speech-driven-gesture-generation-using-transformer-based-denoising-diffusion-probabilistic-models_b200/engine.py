@@ -190,6 +190,7 @@ class SamplingChain:
         self.plan = None
         self.side = th.cuda.Stream(device=device)
         self.concurrent = getattr(model, "concurrent_streams", True)
+        self.encoder_chunk = getattr(model, "encoder_chunk", 16)
         self.graph = None
         self._plan_key = None
         self.Tm = None
@@ -209,8 +210,18 @@ class SamplingChain:
         prev = th.backends.cudnn.allow_tf32, th.backends.cuda.matmul.allow_tf32
         th.backends.cudnn.allow_tf32 = th.backends.cuda.matmul.allow_tf32 = False  # reference math is fp32
         try:
+            # fixed-size micro-batches (last one zero-padded): cuDNN then runs the same algorithm whatever the batch
+            # size, so a clip's conditioning - and with it the whole chain - does not depend on its batch or rank
+            chunk = self.encoder_chunk
+            outs = []
             with th.no_grad():
-                return enc(wavform=wav.float())
+                for lo in range(0, wav.shape[0], chunk):
+                    w = wav[lo:lo + chunk].float()
+                    n = w.shape[0]
+                    if n < chunk:
+                        w = th.cat([w, w.new_zeros(chunk - n, w.shape[1])], dim=0)
+                    outs.append([f[:n] for f in enc(wavform=w)])
+            return tuple(th.cat([o[k] for o in outs], dim=0) for k in range(3))
         finally:
             th.backends.cudnn.allow_tf32, th.backends.cuda.matmul.allow_tf32 = prev
 

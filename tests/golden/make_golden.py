@@ -148,6 +148,37 @@ def config(name):
     print(name, "written", sum(v.nbytes for v in out.values()) / 1e6, "MB raw")
 
 
+def sequence():
+    """Long-form windowed generation through the reference's Generator.generate_sequence (generator.py:80-195):
+    beat-ours, ddim20 spacing (DDIM sampler, the function's default), 5 s of audio -> 100 frames in 3 windows."""
+    mp, d_pose, T, L = ref_params("beat", "ddim20")
+    th.manual_seed(0)
+    model, diffusion, *_ = create_model(d_pose=d_pose, model_params=mp, is_training=False)
+    model.eval()
+    model.load_state_dict(boosted_state_dict(model.state_dict(), seed=1))
+    gen = Generator(model, diffusion)
+    n = 2
+    wav_seqs = synthetic_wav(n, 5 * 16000, seed=41)
+    g = th.Generator().manual_seed(42)
+    init = th.randn(n, 10, d_pose, generator=g)
+    x_Ts = [th.randn(n, d_pose, T, generator=g) for _ in range(3)]
+    feed = iter(x_Ts)
+    real_randn, real_like = th.randn, th.randn_like
+    th.randn = lambda *a, **k: next(feed)          # x_T of each window (generate_sample draws it itself)
+    th.randn_like = lambda x: th.zeros_like(x)      # DDIM eta=0 multiplies this draw by sigma=0
+    try:
+        out = {}
+        for smooth in (True, False):
+            feed = iter(x_Ts)
+            res = gen.generate_sequence(wav_seqs, 16000, d_pose, 20, T, 10, smooth_trans=smooth, trans_factor=0.575,
+                                        init_poses=init, sample_alg="ddim", device="cpu", progress=False)
+            out[f"smooth{int(smooth)}"] = res.numpy()
+    finally:
+        th.randn, th.randn_like = real_randn, real_like
+    np.savez_compressed(os.path.join(HERE, "beat_sequence_golden.npz"), **out)
+    print("sequence written", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     th.set_num_threads(8)
@@ -157,3 +188,5 @@ if __name__ == "__main__":
         config("beat")
     if what in ("tedexp", "all"):
         config("tedexp")
+    if what in ("sequence", "all"):
+        sequence()

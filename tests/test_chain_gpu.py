@@ -95,3 +95,41 @@ def test_short_respaced_chain_vs_oracle(name, alg):
     out2 = gen.generate_sample((N, C, T), wav, noise=x_T, sample_alg=alg, device="cuda", progress=False,
                                noise_tape=tape if alg == "ddpm" else None)
     assert th.equal(out, out2)
+
+
+def test_long_form_beat_4x_length():
+    """BASELINE config 5: the beat model at 4x the config's sequence length (T=160, wav 128 000 -> 127 memory tokens):
+    160-query / 127- and 160-key attention tiles, same weights."""
+    from oracle import ddpm_oracle as orc
+    from gesture_b200.engine import chain_for
+    N, T, L = 2, 160, 128000
+    model, diffusion, C, _, _, params = build("beat", "boost")
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    wav = synthetic_wav(N, L, seed=31)
+    feats = orc.speech_features(sd, wav)
+    assert [f.shape[1] for f in feats] == [125, 124, 126]
+    model.to("cuda")
+    chain = chain_for(model, diffusion, (N, C, T), "ddpm", "cuda", use_graph=False)
+    x_T, _ = noise_tape((N, C, T), 1, seed=2)
+    chain.begin(x_T.cuda(), wav.cuda(), need_tape=False)
+    assert chain.Tm == 127
+    for i in (999, 3):
+        x = th.randn(N, C, T, generator=th.Generator().manual_seed(i))
+        with th.no_grad():
+            ref = orc.denoiser(sd, params.type, params.Decoder.heads, x, th.full((N,), i, dtype=th.long), feats)
+        chain.set_state(x.cuda(), i)
+        chain.step_eager()
+        assert rel_l2(chain.eps, ref) < TOL["bf16"], rel_l2(chain.eps, ref)
+
+
+def test_batch_invariance():
+    """A clip's result must not depend on the batch it is sampled in (what makes clip sharding exact)."""
+    from gesture_b200.generator import Generator
+    model, diffusion, C, T, L, params = build("beat", "boost", respacing="ddim10", device="cuda")
+    gen = Generator(model, diffusion)
+    wav = synthetic_wav(5, L, seed=77)
+    x_T, tape = noise_tape((5, C, T), 10, seed=78)
+    full = gen.generate_sample((5, C, T), wav, noise=x_T, sample_alg="ddpm", device="cuda", progress=False, noise_tape=tape)
+    part = gen.generate_sample((2, C, T), wav[3:], noise=x_T[3:], sample_alg="ddpm", device="cuda", progress=False,
+                               noise_tape=tape[:, 3:])
+    assert th.equal(full[3:], part)

@@ -85,3 +85,29 @@ def test_respaced_and_inpaint_chains_vs_reference(name):
     # in-painted seed frames with trans_factor=None are copied exactly (f=0, m=1): x0 = seed at every step
     out = gen.generate_sample((N, C, T), wav, device="cuda", progress=False, **cases["boost.ddim50_inpaint.final"])
     assert rel_l2(out[:, :seed_len].cpu(), seedp[:, :seed_len]) < 1e-5
+
+
+def test_generate_sequence_vs_reference(monkeypatch):
+    """Long-form windowed generation against the reference's Generator.generate_sequence:
+    3 serial windows, seed-pose in-painting with the trans_factor ramp, optional cross-fade."""
+    import numpy as np
+    from gesture_b200.generator import Generator
+    from util import GOLDEN
+    g = np.load(f"{GOLDEN}/beat_sequence_golden.npz")
+    model, diffusion, C, T, L, params = build("beat", "boost", respacing="ddim20", device="cuda")
+    gen = Generator(model, diffusion)
+    n = 2
+    wav_seqs = synthetic_wav(n, 5 * 16000, seed=41)
+    rg = th.Generator().manual_seed(42)
+    init = th.randn(n, 10, C, generator=rg)
+    x_Ts = [th.randn(n, C, T, generator=rg) for _ in range(3)]
+    for smooth in (True, False):
+        feed = iter(x_Ts)
+        monkeypatch.setattr(th, "randn", lambda *a, **k: next(feed).to(k.get("device", "cpu")))
+        out = gen.generate_sequence(wav_seqs, 16000, C, 20, T, 10, smooth_trans=smooth, trans_factor=0.575, init_poses=init,
+                                    sample_alg="ddim", device="cuda", progress=False)
+        monkeypatch.undo()
+        assert out.shape == (n, 100, C)
+        err = rel_l2(out, g[f"smooth{int(smooth)}"])
+        print(f"[beat] generate_sequence smooth={smooth}: rel-L2 {err:.3e}")
+        assert err < 2e-2, err
