@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "ddpm_math.cuh"
 #include "host_util.h"
+#include <cstdlib>
 
 namespace gd {
 
@@ -185,7 +186,10 @@ __device__ __forceinline__ void epilogue_ddpm_chunk(const GemmParams& p, const D
     }
 }
 
-template <int BN, int MODE>
+// CL = thread-block-cluster size along M (1 or 2).  With CL = 2 the two CTAs of a cluster work on two different
+// m-tiles of the SAME n-tile: each loads half of the W tile and TMA-multicasts it into both CTAs' shared memory,
+// halving the W traffic from L2 (the big GEMMs are bound by operand feed, not by the tensor pipe).
+template <int BN, int MODE, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
@@ -205,10 +209,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+    const int cta_rank = (CL > 1) ? static_cast<int>(cluster_ctarank()) : 0;
+    const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
+    const int m_groups = ((p.M + BLOCK_M - 1) / BLOCK_M + CL - 1) / CL;  // groups of CL consecutive m-tiles
     const int n_tiles = p.N / BN;
-    const int num_tiles = m_tiles * n_tiles;
+    const int num_tiles = m_groups * n_tiles;  // work items per cluster-wide scheduler
     const int k_blocks = p.K / BLOCK_K;
+    // work item `tile` -> this CTA's output tile; an m-tile past the end (odd tile count) is all out-of-bounds:
+    // TMA zero-fills its loads and clips its stores, so the CTA just keeps the cluster protocol going
+#define GD_TILE_M0(tile) ((((tile) / n_tiles) * CL + cta_rank) * BLOCK_M)
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&tmap_a);
@@ -218,7 +227,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], CL);  // every CTA that multicasts into this slot must see it released
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&acc_full_bar[s], 1);
@@ -229,6 +238,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
     tc_fence_before_sync();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // peer barriers are initialised before any multicast can land
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -236,14 +246,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / n_tiles) * BLOCK_M;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                const int m0 = GD_TILE_M0(tile);
                 const int n0 = (tile % n_tiles) * BN;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                     tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K, m0);
-                    tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmap_b, &full_bar[stage], kb * BLOCK_K, n0);
+                    if (CL == 1)
+                        tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmap_b, &full_bar[stage], kb * BLOCK_K, n0);
+                    else  // my 1/CL slice of the W tile, delivered to every CTA of the cluster
+                        tma_load_2d_multicast(smem_b + stage * Cfg::B_BYTES + cta_rank * (Cfg::B_BYTES / CL), &tmap_b,
+                                              &full_bar[stage], kb * BLOCK_K, n0 + cta_rank * (BN / CL),
+                                              static_cast<uint16_t>((1u << CL) - 1));
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -257,7 +272,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(&acc_empty_bar[acc], acc_phase ^ 1);
@@ -273,7 +288,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         // +32 B per UMMA_K step inside the 128-B swizzle row: start-address field += 2
                         umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    // frees the smem slot when these MMAs retire (in every CTA that writes into it)
+                    if (CL == 1)
+                        umma_commit(&empty_bar[stage]);
+                    else
+                        umma_commit_multicast(&empty_bar[stage], static_cast<uint16_t>((1u << CL) - 1));
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -296,8 +315,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         uint8_t* stg = staging + ew * 4096;
         const bool has_bias = p.bias != nullptr;
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int m0 = (tile / n_tiles) * BLOCK_M;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+            const int m0 = GD_TILE_M0(tile);
             const int n0 = (tile % n_tiles) * BN;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
@@ -380,7 +399,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     tc_fence_before_sync();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer can still multicast into it / arrive on its barriers
     if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+#undef GD_TILE_M0
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -403,13 +424,13 @@ static int make_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t rows, ui
                         CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int BN, int MODE>
-static int launch_gemm(const GemmParams& p, const void* A, int lda, const void* W, int ldw, cudaStream_t stream) {
+template <int BN, int MODE, int CL>
+static int launch_gemm_cl(const GemmParams& p, const void* A, int lda, const void* W, int ldw, cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
     CUtensorMap ta, tb, tout;
     int rc = make_tmap_2d_bf16(&ta, A, p.M, p.K, lda, BLOCK_M);
     if (rc) return rc;
-    rc = make_tmap_2d_bf16(&tb, W, p.N, p.K, ldw, BN);
+    rc = make_tmap_2d_bf16(&tb, W, p.N, p.K, ldw, BN / CL);
     if (rc) return rc;
     tout = ta;  // unused unless a TMA epilogue is selected
     if (MODE == MODE_TMA_BF16)
@@ -421,17 +442,47 @@ static int launch_gemm(const GemmParams& p, const void* A, int lda, const void* 
     if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        GD_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GD_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, MODE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::SMEM_BYTES));
         attr_set = true;
     }
     const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
-    const int tiles = m_tiles * (p.N / BN);
-    const int grid = tiles < sm_count() ? tiles : sm_count();
-    gemm_bf16_tn_kernel<BN, MODE><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tout, p);
+    const int work = ((m_tiles + CL - 1) / CL) * (p.N / BN);  // cluster-level work items
+    const int max_clusters = sm_count() / CL;
+    const int grid = (work < max_clusters ? work : max_clusters) * CL;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES, cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    GD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BN, MODE, CL>, ta, tb, tout, p));
     count_launch();
     GD_CUDA_CHECK(cudaGetLastError());
     return GD_OK;
+}
+
+static bool cluster_pairs_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        // Measured on B200 (tedexp N=256): W multicast changes nothing (3.556 vs 3.567 ms of GEMM per step) - the big
+        // GEMMs are limited by what ONE SM can ingest into shared memory (~64 B/clk: 48 KB per k-block vs 512 MMA
+        // cycles), which multicast does not reduce; only cta_group::2 (each SM stores half of W) would.  Kept as an
+        // opt-in experiment: GD_GEMM_CLUSTER=1.
+        const char* e = getenv("GD_GEMM_CLUSTER");
+        on = (e && e[0] == '1') ? 1 : 0;
+    }
+    return on == 1;
+}
+
+// Optional cluster pairs (see cluster_pairs_enabled) for problems with at least two full waves of tiles.
+template <int BN, int MODE>
+static int launch_gemm(const GemmParams& p, const void* A, int lda, const void* W, int ldw, cudaStream_t stream) {
+    const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+    if (BN >= 128 && cluster_pairs_enabled() && m_tiles * (p.N / BN) >= 2 * sm_count())
+        return launch_gemm_cl<BN, MODE, 2>(p, A, lda, W, ldw, stream);
+    return launch_gemm_cl<BN, MODE, 1>(p, A, lda, W, ldw, stream);
 }
 
 static int validate_linear(const gd_linear_desc* d) {
