@@ -11,6 +11,7 @@
 // (tedexp joint attention over [x ; memory], nn.py:105-113) and zero-pads only at the sequence ends.
 #include "common.cuh"
 #include "host_util.h"
+#include <cstdlib>
 
 namespace gd {
 
@@ -125,6 +126,18 @@ __device__ __forceinline__ void conv_stage(__nv_bfloat16* dst, int L, int L_pad,
     }
 }
 
+__device__ __forceinline__ void unpack_bf16x8(const uint4& u, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+__device__ __forceinline__ float4 unpack_bf16x4(const uint2& u) {
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                       __uint_as_float(u.y & 0xffff0000u));
+}
 __device__ __forceinline__ float ex2_approx(float x) {  // MUFU.EX2; -inf -> 0, which is what masked keys need
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
@@ -307,6 +320,328 @@ static int dispatch_kb(const AttnParams& p, int n_clips, cudaStream_t s) {
     return set_error(GD_ERR_INVALID, "gd_dconv_attention: need 0 < keys <= 160 (got %d)", p.Lk);
 }
 
+
+// =====================================================================================================================
+// v2 (bf16 inputs): persistent, TMA-fed.  A work item is (clip, 64-column head group) = one head for d_k = 64, two for
+// d_k = 32.  Thread 0 asks the TMA engine for the item's raw Q/K/V row blocks (dense 128-B rows, one 2-D box per row
+// segment) and the whole CTA meanwhile works on the previous item, so HBM latency never sits in front of the math:
+//     wait(raw full) -> conv3 raw -> cv (bf16, XOR-swizzled 128-B rows) -> sync -> TMA for the next item into raw
+//                    -> QK^T / softmax / PV from cv (mma.sync + ldmatrix) -> sync
+// Two CTAs per SM interleave their conv and MMA phases.  Shared memory per CTA: raw (Lq+2Lk)*128 B + cv
+// (Lq_pad+2*Lk_pad)*128 B + taps, 111 KB for the 138-token joint attention.
+// =====================================================================================================================
+constexpr int ATT2_ROW_BYTES = 128;  // 64 bf16 columns per item row
+
+__device__ __forceinline__ uint32_t cv_off(int row, int chunk) {  // byte offset of 16-B chunk `chunk` of row `row`
+    return static_cast<uint32_t>(row * ATT2_ROW_BYTES + ((chunk ^ (row & 7)) << 4));
+}
+
+struct Attn2Geom {
+    int n_items, groups;  // groups = heads / (64 / d_k)
+    // byte offsets in dynamic smem.  Every raw tensor block is [zero row | L token rows | zero rows up to L_pad+1]:
+    // the zero rows are the conv's "same" padding and are never written by the TMA engine
+    int raw_k_off, raw_v_off, raw_bytes, cv_q_off, cv_k_off, cv_v_off, taps_off, bar_off;
+    uint32_t tx_bytes;
+};
+
+// conv3 of 16 tokens x 4 columns: 18 raw rows (8-byte loads) -> 16 swizzled bf16 rows
+__device__ __forceinline__ void conv_unit16(const uint8_t* src /* raw row p0 (= token p0-1), column group */,
+                                            uint8_t* dst /* cv row p0, 8-byte half selected */, int chunk,
+                                            const float* tp /* w0[8] w1[8] w2[8] b[8] of the chunk, +4 for odd halves */) {
+    const float4 w0 = *reinterpret_cast<const float4*>(tp), w1 = *reinterpret_cast<const float4*>(tp + 8);
+    const float4 w2 = *reinterpret_cast<const float4*>(tp + 16), bb = *reinterpret_cast<const float4*>(tp + 24);
+    uint2 raw[18];
+#pragma unroll
+    for (int s = 0; s < 18; ++s) raw[s] = *reinterpret_cast<const uint2*>(src + s * ATT2_ROW_BYTES);
+    float4 prev = unpack_bf16x4(raw[0]), cur = unpack_bf16x4(raw[1]);
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        const float4 nxt = unpack_bf16x4(raw[s + 2]);
+        uint2 o;
+        o.x = pack_bf16x2(fmaf(w0.x, prev.x, fmaf(w1.x, cur.x, fmaf(w2.x, nxt.x, bb.x))),
+                          fmaf(w0.y, prev.y, fmaf(w1.y, cur.y, fmaf(w2.y, nxt.y, bb.y))));
+        o.y = pack_bf16x2(fmaf(w0.z, prev.z, fmaf(w1.z, cur.z, fmaf(w2.z, nxt.z, bb.z))),
+                          fmaf(w0.w, prev.w, fmaf(w1.w, cur.w, fmaf(w2.w, nxt.w, bb.w))));
+        // p0 is a multiple of 16, so the row's swizzle term is the compile-time (s & 7)
+        *reinterpret_cast<uint2*>(dst + s * ATT2_ROW_BYTES + ((chunk ^ (s & 7)) << 4)) = o;
+        prev = cur;
+        cur = nxt;
+    }
+}
+
+template <int DK, int KB, int MAXT, int MAXREG>
+__global__ void __launch_bounds__(MAXT) __maxnreg__(MAXREG)
+dconv_attention_tma_kernel(const __grid_constant__ CUtensorMap tm_q0, const __grid_constant__ CUtensorMap tm_q1,
+                           const __grid_constant__ CUtensorMap tm_k0, const __grid_constant__ CUtensorMap tm_k1,
+                           const __grid_constant__ CUtensorMap tm_v0, const __grid_constant__ CUtensorMap tm_v1,
+                           const AttnParams p, const Attn2Geom geo) {
+    constexpr int HG = 64 / DK;       // heads per item
+    constexpr int CPH = DK / 8;       // 16-B chunks per head row
+    constexpr int LK_PAD = KB * 16;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    const int Lq = p.Lq, Lk = p.Lk;
+    const int Lq_pad = (Lq + 15) & ~15;
+    uint8_t* raw_q = smem;
+    uint8_t* raw_k = smem + geo.raw_k_off;
+    uint8_t* raw_v = smem + geo.raw_v_off;
+    uint8_t* cv_q = smem + geo.cv_q_off;
+    uint8_t* cv_k = smem + geo.cv_k_off;
+    uint8_t* cv_v = smem + geo.cv_v_off;
+    float* s_taps = reinterpret_cast<float*>(smem + geo.taps_off);  // [3][CPH][w0 8 | w1 8 | w2 8 | b 8]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + geo.bar_off);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        prefetch_tensormap(&tm_q0), prefetch_tensormap(&tm_k0), prefetch_tensormap(&tm_v0);
+        if (p.q_rows[1]) prefetch_tensormap(&tm_q1);
+        if (p.kv_rows[1]) prefetch_tensormap(&tm_k1), prefetch_tensormap(&tm_v1);
+        mbar_init(full_bar, 1);
+        fence_barrier_init();
+    }
+    for (int i = tid; i < 3 * DK * 4; i += nthr) {
+        const int which = i / (DK * 4), r = i % (DK * 4);
+        const int j = r / 32, part = (r % 32) / 8, e = r % 8;  // chunk j, part: tap 0..2 or bias
+        const float* w = which == 0 ? p.wq : (which == 1 ? p.wk : p.wv);
+        const float* b = which == 0 ? p.bq : (which == 1 ? p.bk : p.bv);
+        const int c = j * 8 + e;
+        s_taps[i] = part < 3 ? __ldg(w + c * 3 + part) : __ldg(b + c);
+    }
+    for (int i = tid; i < geo.raw_bytes / 16; i += nthr) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();  // the zero fill is ordered before the TMA writes that follow the barrier
+    __syncthreads();
+
+    auto issue_load = [&](int item) {  // one thread; token rows start at raw row 1
+        const int clip = item / geo.groups, col0 = (item % geo.groups) * 64;
+        mbar_arrive_expect_tx(full_bar, geo.tx_bytes);
+        tma_load_2d(raw_q + ATT2_ROW_BYTES, &tm_q0, full_bar, col0, clip * p.q_rows[0]);
+        if (p.q_rows[1]) tma_load_2d(raw_q + (1 + p.q_rows[0]) * ATT2_ROW_BYTES, &tm_q1, full_bar, col0, clip * p.q_rows[1]);
+        tma_load_2d(raw_k + ATT2_ROW_BYTES, &tm_k0, full_bar, col0, clip * p.kv_rows[0]);
+        tma_load_2d(raw_v + ATT2_ROW_BYTES, &tm_v0, full_bar, col0, clip * p.kv_rows[0]);
+        if (p.kv_rows[1]) {
+            tma_load_2d(raw_k + (1 + p.kv_rows[0]) * ATT2_ROW_BYTES, &tm_k1, full_bar, col0, clip * p.kv_rows[1]);
+            tma_load_2d(raw_v + (1 + p.kv_rows[0]) * ATT2_ROW_BYTES, &tm_v1, full_bar, col0, clip * p.kv_rows[1]);
+        }
+    };
+
+    int item = blockIdx.x;
+    if (tid == 0 && item < geo.n_items) issue_load(item);
+    uint32_t phase = 0;
+    const int g = lane >> 2, t = lane & 3;
+    const int sw = lane & 7;  // every ldmatrix row index below is (multiple of 8) + (lane & 7)
+    const int nsq = Lq_pad / 16, nsk = LK_PAD / 16;
+    const int conv_items = (nsq + 2 * nsk) * 16;
+    const int q_tiles = Lq_pad / 16;
+    // per-lane ldmatrix bases (row part only; the swizzled column part is added per k-step)
+    const uint32_t qrow_u = smem_u32(cv_q) + (lane & 15) * ATT2_ROW_BYTES;
+    const uint32_t krow_u = smem_u32(cv_k) + ((lane & 7) + (lane >> 4) * 8) * ATT2_ROW_BYTES;
+    const uint32_t vrow_u = smem_u32(cv_v) + ((lane & 7) + ((lane >> 3) & 1) * 8) * ATT2_ROW_BYTES;
+    const float scale_log2 = p.scale_log2;
+
+    for (; item < geo.n_items; item += gridDim.x) {
+        const int clip = item / geo.groups, grp = item % geo.groups;
+        mbar_wait(full_bar, phase);
+        phase ^= 1;
+        // ---- depth-wise conv3 over tokens: raw -> cv, one unit = 16 tokens x 4 columns, no boundary predicates
+        for (int it = tid; it < conv_items; it += nthr) {
+            const int hc4 = it & 15, sg = it >> 4;  // 8-byte column group within the 128-B row, 16-row segment
+            const int which = sg < nsq ? 0 : (sg < nsq + nsk ? 1 : 2);
+            const int p0 = (sg - (which == 0 ? 0 : (which == 1 ? nsq : nsq + nsk))) * 16;
+            const uint8_t* src = (which == 0 ? raw_q : (which == 1 ? raw_k : raw_v)) + p0 * ATT2_ROW_BYTES + hc4 * 8;
+            uint8_t* dst = (which == 0 ? cv_q : (which == 1 ? cv_k : cv_v)) + p0 * ATT2_ROW_BYTES + (hc4 & 1) * 8;
+            conv_unit16(src, dst, hc4 >> 1, s_taps + which * DK * 4 + ((hc4 >> 1) % CPH) * 32 + (hc4 & 1) * 4);
+        }
+        __syncthreads();  // cv complete, raw free
+        if (tid == 0 && item + (int)gridDim.x < geo.n_items) issue_load(item + gridDim.x);
+
+        // ---- attention core: one task = (head of the group, 16-query tile)
+        for (int task = warp; task < HG * q_tiles; task += (nthr >> 5)) {
+            const int hh = task / q_tiles, qt = task - hh * q_tiles;
+            const int hc = hh * CPH;
+            float s[KB * 2][4];
+#pragma unroll
+            for (int n = 0; n < KB * 2; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+            const uint32_t qaddr = qrow_u + qt * 16 * ATT2_ROW_BYTES;
+#pragma unroll
+            for (int kk = 0; kk < DK / 16; ++kk) {
+                uint32_t a0, a1, a2, a3;
+                ldsm_x4(qaddr + (((hc + kk * 2 + (lane >> 4)) ^ sw) << 4), a0, a1, a2, a3);
+                const uint32_t kaddr = krow_u + (((hc + kk * 2 + ((lane >> 3) & 1)) ^ sw) << 4);
+#pragma unroll
+                for (int nb = 0; nb < KB; ++nb) {
+                    uint32_t b0, b1, b2, b3;
+                    ldsm_x4(kaddr + nb * 16 * ATT2_ROW_BYTES, b0, b1, b2, b3);
+                    mma_bf16_16816(s[2 * nb], a0, a1, a2, a3, b0, b1);
+                    mma_bf16_16816(s[2 * nb + 1], a0, a1, a2, a3, b2, b3);
+                }
+            }
+            float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+            for (int n = 0; n < KB * 2; ++n) {
+                if (n >= KB * 2 - 2 && n * 8 + 8 > Lk) {
+                    const int j = n * 8 + 2 * t;
+                    if (j >= Lk) s[n][0] = s[n][2] = -INFINITY;
+                    if (j + 1 >= Lk) s[n][1] = s[n][3] = -INFINITY;
+                }
+                m0 = fmaxf(m0, fmaxf(s[n][0], s[n][1]));
+                m1 = fmaxf(m1, fmaxf(s[n][2], s[n][3]));
+            }
+            m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+            m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+            m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+            m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+            const float o0 = m0 * scale_log2, o1 = m1 * scale_log2;
+            float sum0 = 0.f, sum1 = 0.f;
+            uint32_t pk[KB * 2][2];  // P rounded to bf16 right away: halves the live registers going into PV
+#pragma unroll
+            for (int n = 0; n < KB * 2; ++n) {
+                const float e0 = ex2_approx(fmaf(s[n][0], scale_log2, -o0));
+                const float e1 = ex2_approx(fmaf(s[n][1], scale_log2, -o0));
+                const float e2 = ex2_approx(fmaf(s[n][2], scale_log2, -o1));
+                const float e3 = ex2_approx(fmaf(s[n][3], scale_log2, -o1));
+                sum0 += e0 + e1;
+                sum1 += e2 + e3;
+                pk[n][0] = pack_bf16x2(e0, e1);
+                pk[n][1] = pack_bf16x2(e2, e3);
+            }
+            sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+            sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+            sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+            sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+            float o[DK / 8][4];
+#pragma unroll
+            for (int n = 0; n < DK / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+            uint32_t vcol[DK / 16];
+#pragma unroll
+            for (int nb = 0; nb < DK / 16; ++nb) vcol[nb] = vrow_u + (((hc + nb * 2 + (lane >> 4)) ^ sw) << 4);
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+                for (int nb = 0; nb < DK / 16; ++nb) {
+                    uint32_t b0, b1, b2, b3;
+                    ldsm_x4_trans(vcol[nb] + kb * 16 * ATT2_ROW_BYTES, b0, b1, b2, b3);
+                    mma_bf16_16816(o[2 * nb], pk[2 * kb][0], pk[2 * kb][1], pk[2 * kb + 1][0], pk[2 * kb + 1][1], b0, b1);
+                    mma_bf16_16816(o[2 * nb + 1], pk[2 * kb][0], pk[2 * kb][1], pk[2 * kb + 1][0], pk[2 * kb + 1][1], b2, b3);
+                }
+            }
+            const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+            const int col = grp * 64 + hh * DK + 2 * t;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int i = qt * 16 + g + half * 8;
+                if (i < Lq) {
+                    __nv_bfloat16* orow = (i < p.q_rows[0])
+                                              ? p.out[0] + ((size_t)clip * p.q_rows[0] + i) * p.out_ld[0]
+                                              : p.out[1] + ((size_t)clip * p.q_rows[1] + (i - p.q_rows[0])) * p.out_ld[1];
+                    const float inv = half ? inv1 : inv0;
+#pragma unroll
+                    for (int n = 0; n < DK / 8; ++n)
+                        *reinterpret_cast<uint32_t*>(orow + col + n * 8) = pack_bf16x2(o[n][2 * half] * inv, o[n][2 * half + 1] * inv);
+                }
+            }
+        }
+        __syncthreads();  // cv may be overwritten by the next item's conv
+    }
+}
+
+static int make_rows_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    static PFN_encodeTiled encode = get_encode_tiled();
+    if (!encode) return set_error(GD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(GD_ERR_CUDA, "cuTensorMapEncodeTiled (attention) failed (CUresult %d)", (int)r);
+    return GD_OK;
+}
+
+template <int DK, int KB>
+static int launch_attention_tma(const AttnParams& p, int n_clips, cudaStream_t s) {
+    constexpr int HG = 64 / DK;
+    constexpr int MAXT = 256;  // 8 warps x 128 registers: two CTAs fill the register file of an SM exactly
+    constexpr int MAXREG = KB <= 5 ? 96 : 128;  // short key ranges need fewer registers: 20 instead of 16 warps per SM
+    auto kern = dconv_attention_tma_kernel<DK, KB, MAXT, MAXREG>;
+    const int Lq_pad = (p.Lq + 15) & ~15, Lk_pad = KB * 16;
+    Attn2Geom geo{};
+    geo.groups = p.heads / HG;
+    geo.n_items = n_clips * geo.groups;
+    geo.raw_k_off = (Lq_pad + 2) * ATT2_ROW_BYTES;
+    geo.raw_v_off = geo.raw_k_off + (Lk_pad + 2) * ATT2_ROW_BYTES;
+    geo.raw_bytes = geo.raw_v_off + (Lk_pad + 2) * ATT2_ROW_BYTES;
+    geo.cv_q_off = geo.raw_bytes;
+    geo.cv_k_off = geo.cv_q_off + Lq_pad * ATT2_ROW_BYTES;
+    geo.cv_v_off = geo.cv_k_off + Lk_pad * ATT2_ROW_BYTES;
+    geo.taps_off = geo.cv_v_off + Lk_pad * ATT2_ROW_BYTES;
+    geo.bar_off = geo.taps_off + 3 * DK * 4 * (int)sizeof(float);
+    geo.tx_bytes = (uint32_t)(p.Lq + 2 * p.Lk) * ATT2_ROW_BYTES;
+    const size_t smem = (size_t)geo.bar_off + 16 + 128 /*base alignment slack*/;
+    CUtensorMap tq[2], tk[2], tv[2];
+    for (int sgi = 0; sgi < 2; ++sgi) {
+        const int has_q = p.q_rows[sgi] > 0, has_k = p.kv_rows[sgi] > 0;
+        int rc = make_rows_tmap(&tq[sgi], has_q ? p.q[sgi] : p.q[0], (uint64_t)n_clips * p.q_rows[has_q ? sgi : 0],
+                                (uint64_t)p.heads * DK, p.q_ld[has_q ? sgi : 0], p.q_rows[has_q ? sgi : 0]);
+        if (rc) return rc;
+        rc = make_rows_tmap(&tk[sgi], has_k ? p.k[sgi] : p.k[0], (uint64_t)n_clips * p.kv_rows[has_k ? sgi : 0],
+                            (uint64_t)p.heads * DK, p.kv_ld[has_k ? sgi : 0], p.kv_rows[has_k ? sgi : 0]);
+        if (rc) return rc;
+        rc = make_rows_tmap(&tv[sgi], has_k ? p.v[sgi] : p.v[0], (uint64_t)n_clips * p.kv_rows[has_k ? sgi : 0],
+                            (uint64_t)p.heads * DK, p.kv_ld[has_k ? sgi : 0], p.kv_rows[has_k ? sgi : 0]);
+        if (rc) return rc;
+    }
+    static size_t configured = 0;
+    if (smem > configured) {
+        GD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
+        GD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        configured = smem;
+    }
+    // warps: one per (head, 16-query tile) task, but enough of them to make the conv pass of K/V-heavy items quick
+    const int tasks = HG * (Lq_pad / 16);
+    int warps = tasks;
+    const int conv_warps = (Lq_pad + 2 * Lk_pad) / 48;  // ~48 token rows of conv per warp
+    if (warps < conv_warps) warps = conv_warps;
+    if (warps < 4) warps = 4;
+    if (warps > MAXT / 32) warps = MAXT / 32;
+    int per_sm = 0;
+    GD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+    if (per_sm < 1) return set_error(GD_ERR_CUDA, "gd_dconv_attention: kernel does not fit on an SM (smem %zu B)", smem);
+    int grid = per_sm * sm_count();
+    if (grid > geo.n_items) grid = geo.n_items;
+    kern<<<grid, warps * 32, smem, s>>>(tq[0], tq[1], tk[0], tk[1], tv[0], tv[1], p, geo);
+    count_launch();
+    GD_CUDA_CHECK(cudaGetLastError());
+    return GD_OK;
+}
+
+template <int DK>
+static int dispatch_kb_tma(const AttnParams& p, int n_clips, cudaStream_t s) {
+    switch ((p.Lk + 15) / 16) {
+        case 1: return launch_attention_tma<DK, 1>(p, n_clips, s);
+        case 2: return launch_attention_tma<DK, 2>(p, n_clips, s);
+        case 3: return launch_attention_tma<DK, 3>(p, n_clips, s);
+        case 4: return launch_attention_tma<DK, 4>(p, n_clips, s);
+        case 5: return launch_attention_tma<DK, 5>(p, n_clips, s);
+        case 6: return launch_attention_tma<DK, 6>(p, n_clips, s);
+        case 7: return launch_attention_tma<DK, 7>(p, n_clips, s);
+        case 8: return launch_attention_tma<DK, 8>(p, n_clips, s);
+        case 9: return launch_attention_tma<DK, 9>(p, n_clips, s);
+        case 10: return launch_attention_tma<DK, 10>(p, n_clips, s);
+    }
+    return set_error(GD_ERR_INVALID, "gd_dconv_attention: need 0 < keys <= 160 (got %d)", p.Lk);
+}
+
+static int attention_variant() {  // GD_ATTN=v1 selects the per-(clip, head) kernel above (A/B measurements)
+    static int v = 0;
+    if (!v) {
+        const char* e = getenv("GD_ATTN");
+        v = (e && e[0] == 'v' && e[1] == '1') ? 1 : 2;
+    }
+    return v;
+}
+
 static int run_attention(const gd_attn_desc* d, bool fp32_in, void* stream) {
     if (!d) return set_error(GD_ERR_INVALID, "gd_dconv_attention: null descriptor");
     if (!d->q[0] || !d->k[0] || !d->v[0] || !d->out[0]) return set_error(GD_ERR_INVALID, "gd_dconv_attention: segment 0 missing");
@@ -334,6 +669,13 @@ static int run_attention(const gd_attn_desc* d, bool fp32_in, void* stream) {
     if (p.Lq <= 0 || p.Lk <= 0 || p.Lk > 160 || p.Lq > 1024)
         return set_error(GD_ERR_INVALID, "gd_dconv_attention: need 0 < keys <= 160 (got %d), queries <= 1024", p.Lk);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    // bf16 rows whose segments fit a TMA box go to the persistent TMA-fed kernel
+    const bool tma_ok = !fp32_in && attention_variant() == 2 && p.q_rows[0] <= 256 && p.q_rows[1] <= 256 &&
+                        p.Lq <= 256 && (64 % d->d_k) == 0 && d->heads % (64 / d->d_k) == 0;
+    if (tma_ok) {
+        if (d->d_k == 32) return dispatch_kb_tma<32>(p, d->n_clips, s);
+        if (d->d_k == 64) return dispatch_kb_tma<64>(p, d->n_clips, s);
+    }
     if (d->d_k == 32) return fp32_in ? dispatch_kb<float, 32>(p, d->n_clips, s) : dispatch_kb<__nv_bfloat16, 32>(p, d->n_clips, s);
     if (d->d_k == 64) return fp32_in ? dispatch_kb<float, 64>(p, d->n_clips, s) : dispatch_kb<__nv_bfloat16, 64>(p, d->n_clips, s);
     return set_error(GD_ERR_INVALID, "gd_dconv_attention: d_k=%d unsupported (32/64)", d->d_k);

@@ -116,11 +116,17 @@ def _ref_attention(q, k, v, taps, scale):
     return torch.einsum("nhij,njhd->nihd", p, v)
 
 
-@pytest.mark.parametrize("dk,rows_q,rows_kv,f32", [(32, (40, 0), (40, 0), False), (32, (40, 0), (32, 0), False),
-                                                    (64, (34, 104), (34, 104), False), (64, (104, 0), (104, 0), True),
-                                                    (32, (160, 0), (127, 0), False)])
-def test_dconv_attention(gd, dk, rows_q, rows_kv, f32):
-    N, H = 5, 8
+@pytest.mark.parametrize("dk,rows_q,rows_kv,f32,N", [
+    (32, (40, 0), (40, 0), False, 5), (32, (40, 0), (32, 0), False, 5), (64, (34, 104), (34, 104), False, 5),
+    (64, (104, 0), (104, 0), True, 5), (32, (160, 0), (127, 0), False, 5),
+    # last-layer joint attention: pose queries only, keys over [x ; memory]
+    (64, (34, 0), (34, 104), False, 5),
+    # more work items than resident CTAs: the persistent kernel walks several items per CTA (TMA ring reuse)
+    (64, (34, 104), (34, 104), False, 90), (64, (34, 0), (34, 0), False, 300), (32, (40, 0), (40, 0), False, 700),
+    (32, (40, 0), (32, 0), False, 333), (64, (7, 0), (7, 0), False, 3), (32, (160, 0), (160, 0), False, 40),
+    (32, (300, 0), (100, 0), False, 3)])
+def test_dconv_attention(gd, dk, rows_q, rows_kv, f32, N):
+    H = 8
     d_model = H * dk
     g = torch.Generator(device="cuda").manual_seed(dk + sum(rows_q))
     dt = torch.float32 if f32 else torch.bfloat16
