@@ -130,6 +130,31 @@ int gd_layernorm(const float* x, int32_t ldx, const float* gamma, const float* b
                  int32_t M, int32_t D, float eps, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * gd_linear_resid_ln: residual GEMM with the LayerNorm that follows it fused into the epilogue:
+ *
+ *     H   += A · Wᵀ + bias              (d->out_f32 == d->residual: the fp32 residual stream, in place)
+ *     xn   = LayerNorm(H) * gamma + beta  -> bf16
+ *
+ * Replaces `x = x + self.dropout(attn(...))` / `x = x + self.dropout(ff(...))` together with the next
+ * `self.norm_*(x)` of models/nn.py:97-124,158-173 (out-projection `transformer.py:118` or FeedForward layer2
+ * `transformer.py:153`, then nn.LayerNorm([d]) eps 1e-5).  d->N must be the model width (256 or 512) so that a CTA
+ * (pair) owns complete rows.  Rows >= split_row are normalised with (gamma2, beta2): the tedexp joint attention
+ * updates pose rows and memory rows in one GEMM but they feed norm_ff / norm_ff_mem (nn.py:116-123).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gd_ln_desc {
+    const float* gamma;   /* [N] */
+    const float* beta;    /* [N] */
+    const float* gamma2;  /* optional second parameter set for rows >= split_row */
+    const float* beta2;
+    int32_t split_row;
+    void* out_bf16;       /* bf16 [M, N], row stride ldo */
+    int32_t ldo;
+    float eps;
+} gd_ln_desc;
+
+int gd_linear_resid_ln(const gd_linear_desc* d, const gd_ln_desc* ln, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * gd_dconv_attention: MultiDConvHeadAttention core (models/modules/transformer.py:88-126):
  * per (clip, head): Q,K,V = depth-wise conv3 over tokens (SpatialDepthWiseConv :19-44, zero "same"
  * padding, taps shared by all heads) of the already-projected rows, S = softmax_keys(QKᵀ·scale),

@@ -132,6 +132,28 @@ def gemm_case(M, N, K, mode, sets=3):
             "us": round(us, 2), "TFLOPs": round(flops / us * 1e-6, 1), "GBs": round(nbytes / us * 1e-3, 1)}
 
 
+def resid_ln_case(M, N, K, sets=3):
+    lib = gd.load()
+    W = (th.randn(N, K, device="cuda") * 0.05).bfloat16()
+    bias, gam, bet = th.randn(N, device="cuda"), th.rand(N, device="cuda") + 0.5, th.randn(N, device="cuda")
+    fns, keep = [], []
+    for _ in range(sets):
+        A = th.randn(M, K, device="cuda").bfloat16()
+        H = th.zeros(M, N, device="cuda")
+        xn = th.empty(M, N, device="cuda", dtype=th.bfloat16)
+        d = gd.LinearDesc()
+        d.A, d.W, d.M, d.N, d.K, d.lda, d.ldw, d.bias = A.data_ptr(), W.data_ptr(), M, N, K, K, K, bias.data_ptr()
+        d.out_f32, d.ldo_f32, d.residual, d.ldr = H.data_ptr(), N, H.data_ptr(), N
+        ln = gd.LnDesc()
+        ln.gamma, ln.beta, ln.out_bf16, ln.ldo, ln.eps = gam.data_ptr(), bet.data_ptr(), xn.data_ptr(), N, 1e-5
+        keep.append((A, H, xn, d, ln))
+        fns.append(lambda d=d, ln=ln: gd.check(lib.gd_linear_resid_ln(C.byref(d), C.byref(ln), stream()), "resid_ln"))
+    us = time_us(fns)
+    nbytes = 2 * M * K + 2 * N * K + 8 * M * N + 2 * M * N
+    return {"kernel": "gemm_resid_ln", "M": M, "N": N, "K": K, "us": round(us, 2),
+            "TFLOPs": round(2.0 * M * N * K / us * 1e-6, 1), "GBs": round(nbytes / us * 1e-3, 1)}
+
+
 def layernorm_case(M, D, sets=3):
     lib = gd.load()
     g, b = th.randn(D, device="cuda"), th.randn(D, device="cuda")
@@ -148,7 +170,7 @@ def layernorm_case(M, D, sets=3):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["attention", "ddpm", "gemm", "layernorm"])
+    ap.add_argument("what", choices=["attention", "ddpm", "gemm", "layernorm", "resid_ln"])
     ap.add_argument("--out", default=None)
     ap.add_argument("--quick", action="store_true", help="one launch set per case (ncu captures)")
     args = ap.parse_args()
@@ -176,6 +198,10 @@ def main():
                  (40960, 256, 1024, "resid")]
         for c in cases:
             res.append(gemm_case(*c, sets=1 if args.quick else 3))
+    elif args.what == "resid_ln":
+        for M, N, K in [(35328, 512, 512), (26624, 512, 512), (8704, 512, 512), (35328, 512, 2048), (26624, 512, 2048),
+                        (8704, 512, 2048), (40960, 256, 256), (40960, 256, 1024)]:
+            res.append(resid_ln_case(M, N, K, sets=1 if args.quick else 3))
     else:
         for M, D in [(35328, 512), (26624, 512), (8704, 512), (40960, 256)]:
             res.append(layernorm_case(M, D, sets=1 if args.quick else 3))

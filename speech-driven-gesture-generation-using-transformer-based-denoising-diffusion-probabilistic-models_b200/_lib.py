@@ -27,6 +27,11 @@ class DdpmDesc(C.Structure):
                 ("inpaint_seed", c_vp), ("inpaint_mask", c_vp), ("inpaint_factor", c_vp), ("clip_x0", c_f32)]
 
 
+class LnDesc(C.Structure):
+    _fields_ = [("gamma", c_vp), ("beta", c_vp), ("gamma2", c_vp), ("beta2", c_vp), ("split_row", c_i32),
+                ("out_bf16", c_vp), ("ldo", c_i32), ("eps", c_f32)]
+
+
 class AttnDesc(C.Structure):
     _fields_ = [("q", c_vp * 2), ("q_rows", c_i32 * 2), ("q_ld", c_i32 * 2), ("k", c_vp * 2), ("v", c_vp * 2),
                 ("kv_rows", c_i32 * 2), ("kv_ld", c_i32 * 2), ("out", c_vp * 2), ("out_ld", c_i32 * 2),
@@ -44,6 +49,7 @@ SYMBOLS = {
     "gd_linear_bf16": (c_i32, [C.POINTER(LinearDesc), c_vp]),
     "gd_ddpm_update": (c_i32, [C.POINTER(DdpmDesc), c_vp, c_vp]),
     "gd_linear_ddpm": (c_i32, [C.POINTER(LinearDesc), C.POINTER(DdpmDesc), c_vp]),
+    "gd_linear_resid_ln": (c_i32, [C.POINTER(LinearDesc), C.POINTER(LnDesc), c_vp]),
     "gd_layernorm": (c_i32, [c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_f32, c_vp]),
     "gd_dconv_attention": (c_i32, [C.POINTER(AttnDesc), c_vp]),
     "gd_dconv_attention_f32in": (c_i32, [C.POINTER(AttnDesc), c_vp]),

@@ -47,13 +47,18 @@ struct GemmParams {
     gd_ddpm_desc ddpm;
 };
 
-template <int BN>
+template <int BN, int CL>
 struct GemmCfg {
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-    static constexpr int B_BYTES = BN * BLOCK_K * 2;
+    static constexpr int B_BYTES = (BN / CL) * BLOCK_K * 2;  // a CTA of a pair stores half of the W tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-    static constexpr int STAGING_BYTES = EPI_WARPS * 32 * 32 * 4;  // per epilogue warp: 32 rows x 32 fp32 columns
+    // per epilogue warp one 32-row x 32-column fp32 staging tile.  A deeper ring and a shared-memory copy of the bias were
+    // measured and changed nothing (the epilogue is not waiting on them) while costing a pipeline stage, so: 4 KB / warp.
+    static constexpr int STAGING_PER_WARP = 4096;
+    static constexpr int STAGING_BYTES = EPI_WARPS * STAGING_PER_WARP;
+    static constexpr int SMEM_LIMIT = 227 * 1024;
+    static constexpr int STAGES_FIT = (SMEM_LIMIT - 2048 - STAGING_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*barriers*/ + STAGING_BYTES + 1024 /*align slack*/;
     static constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
 };
@@ -186,14 +191,15 @@ __device__ __forceinline__ void epilogue_ddpm_chunk(const GemmParams& p, const D
     }
 }
 
-// CL = thread-block-cluster size along M (1 or 2).  With CL = 2 the two CTAs of a cluster work on two different
-// m-tiles of the SAME n-tile: each loads half of the W tile and TMA-multicasts it into both CTAs' shared memory,
-// halving the W traffic from L2 (the big GEMMs are bound by operand feed, not by the tensor pipe).
+// CL = 1: one CTA per 128 x BN tile.  CL = 2: a CTA pair (cta_group::2) owns a 256 x BN tile - each CTA stages its own
+// 128 rows of A and HALF of the W tile, the leader CTA issues one M=256 MMA that reads both halves, and every CTA
+// keeps the accumulator rows of its own m-tile in its own TMEM.  The big GEMMs are bound by what an SM can ingest
+// from L2 (~42 B/clk measured: 48 KB per k-block vs 512 MMA clocks); pairing cuts that to 32 KB per k-block.
 template <int BN, int MODE, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, CL>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -226,19 +232,24 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], CL);  // every CTA that multicasts into this slot must see it released
+            mbar_init(&full_bar[s], 1);   // CL = 2: only the leader's is used (both CTAs' TMA bytes land on it)
+            mbar_init(&empty_bar[s], 1);  // released by the (pair-wide) MMA commit
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&acc_full_bar[s], 1);
-            mbar_init(&acc_empty_bar[s], EPI_WARPS);  // one arrive per epilogue warp
+            mbar_init(&acc_empty_bar[s], CL * EPI_WARPS);  // one arrive per epilogue warp of every CTA of the pair
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    if (warp == 2) {
+        if (CL == 1)
+            tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+        else
+            tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
+    }
     tc_fence_before_sync();
     __syncthreads();
-    if (CL > 1) cluster_sync_all();  // peer barriers are initialised before any multicast can land
+    if (CL > 1) cluster_sync_all();  // the peer's barriers and TMEM exist before any cross-CTA traffic
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -251,14 +262,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const int n0 = (tile % n_tiles) * BN;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                    tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K, m0);
-                    if (CL == 1)
+                    if (CL == 1) {
+                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                        tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K, m0);
                         tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmap_b, &full_bar[stage], kb * BLOCK_K, n0);
-                    else  // my 1/CL slice of the W tile, delivered to every CTA of the cluster
-                        tma_load_2d_multicast(smem_b + stage * Cfg::B_BYTES + cta_rank * (Cfg::B_BYTES / CL), &tmap_b,
-                                              &full_bar[stage], kb * BLOCK_K, n0 + cta_rank * (BN / CL),
-                                              static_cast<uint16_t>((1u << CL) - 1));
+                    } else {
+                        // both CTAs fill their own slot; all bytes are counted on the leader's barrier
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], CL * Cfg::STAGE_BYTES);
+                        const uint32_t lead_bar = map_to_cta(smem_u32(&full_bar[stage]), 0);
+                        tma_load_2d_pair(smem_a + stage * Cfg::A_BYTES, &tmap_a, lead_bar, kb * BLOCK_K, m0);
+                        tma_load_2d_pair(smem_b + stage * Cfg::B_BYTES, &tmap_b, lead_bar, kb * BLOCK_K,
+                                         n0 + cta_rank * (BN / CL));
+                    }
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -267,8 +282,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN);
+        if (lane == 0 && cta_rank == 0) {  // the leader CTA issues the MMAs of the whole pair
+            constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M * CL, BN);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -286,19 +301,25 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         // +32 B per UMMA_K step inside the 128-B swizzle row: start-address field += 2
-                        umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (CL == 1)
+                            umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        else
+                            umma_bf16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    // frees the smem slot when these MMAs retire (in every CTA that writes into it)
+                    // frees the smem slot (of both CTAs of a pair) when these MMAs retire
                     if (CL == 1)
                         umma_commit(&empty_bar[stage]);
                     else
-                        umma_commit_multicast(&empty_bar[stage], static_cast<uint16_t>((1u << CL) - 1));
+                        umma_commit_pair(&empty_bar[stage], 0b11);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                umma_commit(&acc_full_bar[acc]);  // accumulator complete -> epilogue
+                if (CL == 1)  // accumulator complete -> epilogue (of both CTAs of a pair)
+                    umma_commit(&acc_full_bar[acc]);
+                else
+                    umma_commit_pair(&acc_full_bar[acc], 0b11);
             }
         }
     } else if (warp >= 4) {
@@ -312,7 +333,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             t = *p.ddpm.step_ptr;
             cf = ddpm_load_coefs(p.ddpm, t);
         }
-        uint8_t* stg = staging + ew * 4096;
+        uint8_t* stg_base = staging + ew * Cfg::STAGING_PER_WARP;
+        constexpr int STG_CHUNK = (MODE == MODE_TMA_F32) ? 4096 : 2048;
+        constexpr int STG_RING = Cfg::STAGING_PER_WARP / STG_CHUNK;
+        uint32_t chunk_ctr = 0;  // chunks this warp has handed to the TMA engine
         const bool has_bias = p.bias != nullptr;
         int it = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
@@ -351,8 +375,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                         for (int j = 0; j < 32; ++j) r[j] = apply_act(r[j], GD_ACT_SILU);
                     }
-                    // the previous TMA store of this warp must have finished READING the staging tile
-                    if (lane == 0) bulk_wait_group_read0();
+                    // ring slot: the store issued STG_RING chunks ago must have finished READING it
+                    uint8_t* stg = stg_base + (chunk_ctr % STG_RING) * STG_CHUNK;
+                    ++chunk_ctr;
+                    if (lane == 0) bulk_wait_group_read<STG_RING - 1>();
                     __syncwarp();
                     if (MODE == MODE_TMA_F32) {
                         float4* st4 = reinterpret_cast<float4*>(stg);  // 128-B rows, SWIZZLE_128B: chunk ^= row & 7
@@ -392,7 +418,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty_bar[acc]);
+            if (lane == 0) {
+                if (CL == 1)
+                    mbar_arrive(&acc_empty_bar[acc]);
+                else  // the MMA issuer lives in the leader CTA
+                    mbar_arrive_cluster(map_to_cta(smem_u32(&acc_empty_bar[acc]), 0));
+            }
         }
         if ((MODE == MODE_TMA_BF16 || MODE == MODE_TMA_F32) && lane == 0) bulk_wait_group0();
     }
@@ -400,13 +431,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tc_fence_before_sync();
     __syncthreads();
     if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer can still multicast into it / arrive on its barriers
-    if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (warp == 2) {
+        if (CL == 1)
+            tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+        else
+            tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+    }
 #undef GD_TILE_M0
 }
 
 // ------------------------------------------------------------------------------------------ host
-static int make_tmap_2d(CUtensorMap* m, CUtensorMapDataType dt, int elt_bytes, const void* base, uint64_t rows,
-                        uint64_t cols, uint64_t ld_elems, uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swz) {
+int make_tmap_2d(CUtensorMap* m, CUtensorMapDataType dt, int elt_bytes, const void* base, uint64_t rows, uint64_t cols,
+                 uint64_t ld_elems, uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swz) {
     static PFN_encodeTiled encode = get_encode_tiled();
     if (!encode) return set_error(GD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     cuuint64_t dims[2] = {cols, rows};
@@ -426,7 +462,7 @@ static int make_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t rows, ui
 
 template <int BN, int MODE, int CL>
 static int launch_gemm_cl(const GemmParams& p, const void* A, int lda, const void* W, int ldw, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, CL>;
     CUtensorMap ta, tb, tout;
     int rc = make_tmap_2d_bf16(&ta, A, p.M, p.K, lda, BLOCK_M);
     if (rc) return rc;
@@ -463,24 +499,21 @@ static int launch_gemm_cl(const GemmParams& p, const void* A, int lda, const voi
     return GD_OK;
 }
 
-static bool cluster_pairs_enabled() {
-    static int on = -1;
-    if (on < 0) {
-        // Measured on B200 (tedexp N=256): W multicast changes nothing (3.556 vs 3.567 ms of GEMM per step) - the big
-        // GEMMs are limited by what ONE SM can ingest into shared memory (~64 B/clk: 48 KB per k-block vs 512 MMA
-        // cycles), which multicast does not reduce; only cta_group::2 (each SM stores half of W) would.  Kept as an
-        // opt-in experiment: GD_GEMM_CLUSTER=1.
-        const char* e = getenv("GD_GEMM_CLUSTER");
-        on = (e && e[0] == '1') ? 1 : 0;
-    }
-    return on == 1;
+// GD_GEMM_PAIR: 0 = never pair, 2 = pair whenever the shape allows (tests, A/B runs); default = long K only.
+static int cta_pair_policy() {
+    const char* e = getenv("GD_GEMM_PAIR");
+    return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
 }
 
-// Optional cluster pairs (see cluster_pairs_enabled) for problems with at least two full waves of tiles.
+// CTA pairs (256 x BN tiles).  Measured on B200 (profiles/r01_kernel_bench_*.jsonl): +7 % on the K = 2048 down-projections
+// (69 vs 74 us), nothing at K = 512 (the tile is then bound by its epilogue/output traffic, as cuBLAS is: 1.07 PFLOP/s
+// there for both), slower at K = 256 - so pairs are used for long K only.
 template <int BN, int MODE>
 static int launch_gemm(const GemmParams& p, const void* A, int lda, const void* W, int ldw, cudaStream_t stream) {
     const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
-    if (BN >= 128 && cluster_pairs_enabled() && m_tiles * (p.N / BN) >= 2 * sm_count())
+    const int policy = cta_pair_policy();
+    if (BN >= 128 && MODE != MODE_DDPM && MODE != MODE_DIRECT && policy > 0 && (p.K >= 1024 || policy == 2) &&
+        ((m_tiles + 1) / 2) * (p.N / BN) >= sm_count() / 2)
         return launch_gemm_cl<BN, MODE, 2>(p, A, lda, W, ldw, stream);
     return launch_gemm_cl<BN, MODE, 1>(p, A, lda, W, ldw, stream);
 }

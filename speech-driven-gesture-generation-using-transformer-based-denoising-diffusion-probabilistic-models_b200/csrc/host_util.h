@@ -16,6 +16,9 @@ int sm_count();                                 // SMs of the current device (14
 int check_device();                             // GD_OK iff current device is compute capability 10.x
 void count_launch();
 int validate_ddpm(const gd_ddpm_desc* u);
+// 2-D row-major tensor map: box = box_rows x box_cols elements, innermost dimension = columns (gemm_tcgen05.cu)
+int make_tmap_2d(CUtensorMap* m, CUtensorMapDataType dt, int elt_bytes, const void* base, uint64_t rows, uint64_t cols,
+                 uint64_t ld_elems, uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swz);
 
 #define GD_CUDA_CHECK(expr)                                                                          \
     do {                                                                                             \

@@ -139,6 +139,20 @@ class _Launcher:
         return Op(lambda: gd.check(lib.gd_linear_bf16(C.byref(d), self.stream()), "gd_linear_bf16"), "gemm",
                   2 * M * N * (k_alg or K), nbytes)
 
+    def linear_resid_ln(self, A, W, M, N, K, bias, H, ln, xn, ln2=None, split=0):
+        """H += A·Wᵀ + bias (in place, fp32) and xn = LayerNorm(H)·gamma + beta (bf16) in one launch; rows >= split use ln2."""
+        d = gd.LinearDesc()
+        d.A, d.W, d.M, d.N, d.K, d.lda, d.ldw = _p(A), _p(W), M, N, K, A.stride(0), W.stride(0)
+        d.bias, d.residual, d.ldr, d.out_f32, d.ldo_f32 = _p(bias), _p(H), H.stride(0), _p(H), H.stride(0)
+        l = gd.LnDesc()
+        l.gamma, l.beta, l.out_bf16, l.ldo, l.eps = _p(ln[0]), _p(ln[1]), _p(xn), xn.stride(0), 1e-5
+        if ln2 is not None:
+            l.gamma2, l.beta2, l.split_row = _p(ln2[0]), _p(ln2[1]), split
+        lib = self.lib
+        nbytes = 2 * M * K + 2 * N * K + 8 * M * N + 2 * M * N
+        return Op(lambda: gd.check(lib.gd_linear_resid_ln(C.byref(d), C.byref(l), self.stream()), "gd_linear_resid_ln"),
+                  "gemm_ln", 2 * M * N * K + 8 * M * N, nbytes)
+
     def layernorm(self, x, gamma_beta, out, M, D):
         lib, g, b = self.lib, gamma_beta[0], gamma_beta[1]
         args = (_p(x), x.stride(0), _p(g), _p(b), _p(out), out.stride(0), M, D, 1e-5)
@@ -190,6 +204,7 @@ class SamplingChain:
         self.plan = None
         self.side = th.cuda.Stream(device=device)
         self.concurrent = getattr(model, "concurrent_streams", True)
+        self.fuse_ln = getattr(model, "fuse_layernorm", True)  # residual GEMM + following LayerNorm in one kernel
         self.encoder_chunk = getattr(model, "encoder_chunk", 16)
         self.graph = None
         self._plan_key = None
@@ -282,8 +297,9 @@ class SamplingChain:
         u.clip_x0 = 0.0
         return u
 
-    def _attn_block(self, ops, a, rows_lo, rows_hi, segs, xn, qkv, ao, H, n_heads):
-        """LN'd rows [lo,hi) -> fused QKV GEMM -> dconv attention over `segs` -> out-proj + residual into H."""
+    def _attn_block(self, ops, a, rows_lo, rows_hi, segs, xn, qkv, ao, H, n_heads, next_ln=None):
+        """LN'd rows [lo,hi) -> fused QKV GEMM -> dconv attention over `segs` -> out-proj + residual into H
+        (+ the LayerNorm that follows, `next_ln`, written to the same rows of xn)."""
         d, L = self.W.d, self.L
         M = rows_hi - rows_lo
         okw = "out_f32" if self.f32act else "out_bf16"
@@ -293,15 +309,28 @@ class SamplingChain:
         v = [(qkv[lo:, 2 * d:], r) for lo, r in segs]
         o = [(ao[lo:], r) for lo, r in segs]
         ops.append(L.attention(self.N, n_heads, d // n_heads, q, k, v, o, a["taps"], self.f32act))
-        ops.append(L.linear(ao[rows_lo:rows_hi], a["wo"], M, d, d, bias=a["bo"], residual=H[rows_lo:rows_hi],
-                            out_f32=H[rows_lo:rows_hi]))
+        self._resid(ops, ao[rows_lo:rows_hi], a["wo"], a["bo"], M, d, H[rows_lo:rows_hi], next_ln, xn[rows_lo:rows_hi])
 
-    def _ffn_block(self, ops, f, ln, lo, hi, xn, hid, H):
+    def _resid(self, ops, A, W, bias, M, K, H, ln, xn, ln2=None, split=0):
+        """Residual GEMM H += A·Wᵀ + b, fused with the following LayerNorm when `ln` is given (and fusion is on)."""
+        d, L = self.W.d, self.L
+        if ln is not None and self.fuse_ln:
+            ops.append(L.linear_resid_ln(A, W, M, d, K, bias, H, ln, xn, ln2=ln2, split=split))
+            return
+        ops.append(L.linear(A, W, M, d, K, bias=bias, residual=H, out_f32=H))
+        if ln is not None:
+            if ln2 is None or split >= M:
+                ops.append(L.layernorm(H, ln, xn, M, d))
+            else:
+                ops.append(L.layernorm(H[:split], ln, xn[:split], split, d))
+                ops.append(L.layernorm(H[split:], ln2, xn[split:], M - split, d))
+
+    def _ffn_block(self, ops, f, lo, hi, xn, hid, H, next_ln=None):
+        """xn rows [lo,hi) already hold LN(H): up-projection + ReLU², down-projection + residual (+ the next LayerNorm)."""
         d, L = self.W.d, self.L
         M = hi - lo
-        ops.append(L.layernorm(H[lo:hi], ln, xn[lo:hi], M, d))
         ops.append(L.linear(xn[lo:hi], f["w1"], M, 4 * d, d, bias=f["b1"], act=gd.ACT_RELU2, out_bf16=hid[lo:hi]))
-        ops.append(L.linear(hid[lo:hi], f["w2"], M, d, 4 * d, bias=f["b2"], residual=H[lo:hi], out_f32=H[lo:hi]))
+        self._resid(ops, hid[lo:hi], f["w2"], f["b2"], M, 4 * d, H[lo:hi], next_ln, xn[lo:hi])
 
     def _build_plan(self, cond):
         W, L, N, T, d, dev = self.W, self.L, self.N, self.T, self.W.d, self.device
@@ -332,19 +361,22 @@ class SamplingChain:
             ops.append(L.linear(self.xa, W.embx_w, Mx, d, _POSE_PAD, bias=W.embx_b, rowbias=W.pe, period=T, offset=0,
                                 out_f32=X, k_alg=self.C))
             tag(len(ops) - 1, region, 0)
+            # Every LayerNorm except the first of each stream is produced by the residual GEMM in front of it.
+            ops.append(L.layernorm(X, W.layers[0]["ln_sa"], xn[:Mx], Mx, d))
+            tag(len(ops) - 1, region, 0)
+            ops.append(L.layernorm(Mem, W.layers[0]["ln_sam"], xn[Mx:], Mm, d))
+            tag(len(ops) - 1, region, 1)
             for li, ly in enumerate(W.layers):
                 last = li == W.n_layers - 1
+                nxt = None if last else W.layers[li + 1]
                 s0 = len(ops)
-                ops.append(L.layernorm(X, ly["ln_sa"], xn[:Mx], Mx, d))
-                self._attn_block(ops, ly["sa"], 0, Mx, [(0, T)], xn, qkv, ao, H, heads)
+                self._attn_block(ops, ly["sa"], 0, Mx, [(0, T)], xn, qkv, ao, H, heads, next_ln=ly["ln_ca"])
                 tag(s0, region, 0)
                 s0 = len(ops)
-                ops.append(L.layernorm(Mem, ly["ln_sam"], xn[Mx:], Mm, d))
-                self._attn_block(ops, ly["sam"], Mx, R, [(Mx, Tm)], xn, qkv, ao, H, heads)
+                self._attn_block(ops, ly["sam"], Mx, R, [(Mx, Tm)], xn, qkv, ao, H, heads, next_ln=ly["ln_ca"])
                 tag(s0, region, 1)
                 region += 1
                 # joint attention over [x ; memory] (nn.py:105-113); last layer only the pose rows are read afterwards
-                ops.append(L.layernorm(H, ly["ln_ca"], xn, R, d))
                 a = ly["ca"]
                 okw = "out_f32" if self.f32act else "out_bf16"
                 ops.append(L.linear(xn, a["wqkv"], R, 3 * d, d, bias=a["bqkv"], **{okw: qkv}))
@@ -355,13 +387,14 @@ class SamplingChain:
                 vs = [(qkv[lo:, 2 * d:], r) for lo, r in segs]
                 ops.append(L.attention(N, heads, d // heads, qs, ks, vs, os_, a["taps"], self.f32act))
                 Ro = Mx if last else R
-                ops.append(L.linear(ao[:Ro], a["wo"], Ro, d, d, bias=a["bo"], residual=H[:Ro], out_f32=H[:Ro]))
+                self._resid(ops, ao[:Ro], a["wo"], a["bo"], Ro, d, H[:Ro], ly["ln_ff"], xn[:Ro],
+                            ln2=ly.get("ln_ffm"), split=Mx)
                 s0 = len(ops)
-                self._ffn_block(ops, ly["ff"], ly["ln_ff"], 0, Mx, xn, hid, H)
+                self._ffn_block(ops, ly["ff"], 0, Mx, xn, hid, H, next_ln=(W.out_ln if last else nxt["ln_sa"]))
                 if "ffm" in ly:
                     tag(s0, region, 0)
                     s0 = len(ops)
-                    self._ffn_block(ops, ly["ffm"], ly["ln_ffm"], Mx, R, xn, hid, H)
+                    self._ffn_block(ops, ly["ffm"], Mx, R, xn, hid, H, next_ln=(None if last else nxt["ln_sam"]))
                     tag(s0, region, 1)
         else:
             X = th.empty(Mx, d, device=dev)
@@ -383,19 +416,19 @@ class SamplingChain:
             ops.append(L.linear(self.xa, W.embx_w, Mx, d, _POSE_PAD, bias=W.embx_b, rowbias=W.pe, period=T, offset=0,
                                 out_f32=X, k_alg=self.C))
             okw = "out_f32" if self.f32act else "out_bf16"
+            ops.append(L.layernorm(X, W.layers[0]["ln_sa"], xn, Mx, d))
             for li, ly in enumerate(W.layers):
-                ops.append(L.layernorm(X, ly["ln_sa"], xn, Mx, d))
-                self._attn_block(ops, ly["sa"], 0, Mx, [(0, T)], xn, qkv, ao, H, heads)
+                last = li == W.n_layers - 1
+                self._attn_block(ops, ly["sa"], 0, Mx, [(0, T)], xn, qkv, ao, H, heads, next_ln=ly["ln_ca"])
                 # cross attention: queries from the pose rows, K|V hoisted per chain (memory is never updated, nn.py:160-162)
                 a = ly["ca"]
-                ops.append(L.layernorm(X, ly["ln_ca"], xn, Mx, d))
                 ops.append(L.linear(xn, a["wqkv"][:d], Mx, d, d, bias=a["bqkv"][:d], **{okw: qkv[:, :d]}))
                 kcol = li * 2 * d
                 ops.append(L.attention(N, heads, d // heads, [(qkv[:, 0:], T)], [(kv[:, kcol:], Tm)], [(kv[:, kcol + d:], Tm)],
                                        [(ao, T)], a["taps"], self.f32act))
-                ops.append(L.linear(ao, a["wo"], Mx, d, d, bias=a["bo"], residual=X, out_f32=X))
-                self._ffn_block(ops, ly["ff"], ly["ln_ff"], 0, Mx, xn, hid, H)
-        ops.append(L.layernorm(X, W.out_ln, xn[:Mx], Mx, d))
+                self._resid(ops, ao, a["wo"], a["bo"], Mx, d, X, ly["ln_ff"], xn)
+                self._ffn_block(ops, ly["ff"], 0, Mx, xn, hid, H, next_ln=(W.out_ln if last else W.layers[li + 1]["ln_sa"]))
+        # xn[:Mx] holds out_layers.0 LayerNorm(x) (written by the last down-projection)
         dd = gd.LinearDesc()
         dd.A, dd.W, dd.M, dd.N, dd.K, dd.lda, dd.ldw, dd.bias = _p(xn), _p(W.out_w), Mx, _POSE_PAD, d, d, d, _p(W.out_b)
         self._ddpm = self._ddpm_desc()

@@ -32,7 +32,7 @@ def _linear(gd, A, W, bias=None, rowbias=None, period=0, offset=0, residual=None
 
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (128, 128, 64), (256, 256, 128), (5120, 256, 256), (1000, 768, 256),
                                    (8704, 1536, 512), (8704, 512, 2048), (35328, 512, 512), (77, 128, 128),
-                                   (40960, 1024, 256), (20000, 2048, 512)])
+                                   (40960, 1024, 256), (20000, 2048, 512), (9500, 1024, 128), (19000, 128, 64)])
 def test_linear_plain(gd, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
@@ -72,6 +72,64 @@ def test_linear_epilogue(gd):
     gd.check(gd.load().gd_linear_bf16(C.byref(d), _stream()))
     torch.cuda.synchronize()
     assert (x - (base + res)).abs().max().item() < 5e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(20000, 512, 256), (9500, 1024, 128), (35328, 512, 2048)])
+def test_linear_pair_tiles_epilogues(gd, M, N, K, monkeypatch):
+    monkeypatch.setenv("GD_GEMM_PAIR", "2")  # the default policy pairs CTAs only for K >= 1024
+    _pair_tiles_epilogues(gd, M, N, K)
+
+
+def _pair_tiles_epilogues(gd, M, N, K):
+    """Shapes large enough for the CTA-pair (cta_group::2, 256-row tile) path, odd m-tile counts included: bf16 output
+    with bias + squared ReLU through TMA stores, and the in-place fp32 residual through TMA reduce-add."""
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    base = A.float() @ W.float().t() + bias
+    _, o16 = _linear(gd, A, W, bias=bias, act=gd.ACT_RELU2, want_f32=False, want_bf16=True)
+    ref = torch.relu(base) ** 2
+    assert (o16.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+    res = torch.randn(M, N, device="cuda", generator=g)
+    x = res.clone()
+    d = gd.LinearDesc()
+    d.A, d.W, d.M, d.N, d.K, d.lda, d.ldw = A.data_ptr(), W.data_ptr(), M, N, K, K, K
+    d.bias, d.residual, d.ldr, d.out_f32, d.ldo_f32 = bias.data_ptr(), x.data_ptr(), N, x.data_ptr(), N
+    gd.check(gd.load().gd_linear_bf16(C.byref(d), _stream()))
+    torch.cuda.synchronize()
+    assert (x - (base + res)).abs().max().item() < 5e-3 * max(1.0, base.abs().max().item())
+
+
+@pytest.mark.parametrize("M,N,K,split", [(35328, 512, 512, 8704), (8704, 512, 2048, None), (40960, 256, 256, None),
+                                           (777, 512, 64, 300), (130, 256, 1024, 129), (20000, 256, 1024, None)])
+def test_linear_resid_layernorm_fused(gd, M, N, K, split):
+    """H += A·Wᵀ + b with the following LayerNorm in the epilogue (two parameter sets split by row), vs torch fp32."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    H = torch.randn(M, N, device="cuda", generator=g) * 2.0 + 3.0  # non-zero mean: exercises the shifted sums
+    gam = [torch.rand(N, device="cuda", generator=g) + 0.5 for _ in range(2)]
+    bet = [torch.randn(N, device="cuda", generator=g) for _ in range(2)]
+    ref_h = H + (A.float() @ W.float().t() + bias)
+    ref_n = torch.nn.functional.layer_norm(ref_h, (N,), gam[0], bet[0], 1e-5)
+    if split is not None:
+        ref_n[split:] = torch.nn.functional.layer_norm(ref_h[split:], (N,), gam[1], bet[1], 1e-5)
+    xn = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    d = gd.LinearDesc()
+    d.A, d.W, d.M, d.N, d.K, d.lda, d.ldw = A.data_ptr(), W.data_ptr(), M, N, K, K, K
+    d.bias, d.residual, d.ldr, d.out_f32, d.ldo_f32 = bias.data_ptr(), H.data_ptr(), N, H.data_ptr(), N
+    ln = gd.LnDesc()
+    ln.gamma, ln.beta, ln.out_bf16, ln.ldo, ln.eps = gam[0].data_ptr(), bet[0].data_ptr(), xn.data_ptr(), N, 1e-5
+    if split is not None:
+        ln.gamma2, ln.beta2, ln.split_row = gam[1].data_ptr(), bet[1].data_ptr(), split
+    gd.check(gd.load().gd_linear_resid_ln(C.byref(d), C.byref(ln), _stream()), "gd_linear_resid_ln")
+    torch.cuda.synchronize()
+    assert (H - ref_h).abs().max().item() < 5e-3 * max(1.0, ref_h.abs().max().item())
+    # bf16 output: within one bf16 ulp of the fp32 LayerNorm
+    assert ((xn.float() - ref_n).abs() <= ref_n.abs() * 2 ** -7 + 2e-2).all()
+    assert (xn.float() - ref_n).abs().max().item() < 6e-2
 
 
 def test_linear_rejects_bad_shapes(gd):
