@@ -72,6 +72,9 @@ def diffusion_tables(betas):
         "betas": betas,
         "alphas_cumprod": ac,
         "alphas_cumprod_prev": ac_prev,
+        "sqrt_alphas_cumprod": np.sqrt(ac),
+        "sqrt_one_minus_alphas_cumprod": np.sqrt(1.0 - ac),
+        "log_one_minus_alphas_cumprod": np.log(1.0 - ac),
         "sqrt_recip_alphas_cumprod": np.sqrt(1.0 / ac),
         "sqrt_recipm1_alphas_cumprod": np.sqrt(1.0 / ac - 1.0),
         "posterior_variance": post_var,
@@ -355,3 +358,36 @@ def sample_chain(sd, model_type, heads, tabs, x_T, wav, tape, alg="ddpm", steps=
             record(i, x, eps, x_next)
         x = x_next
     return x
+
+
+@torch.no_grad()
+def bpd_loop(sd, model_type, heads, tabs, x_start, wav, tape):
+    """calc_bpd_loop + _vb_terms_bpd + _prior_bpd - gaussian_diffusion.py:571-678 with losses.py:6-56.
+    x_start (N,C,T); tape[k] is the k-th randn_like draw (loop order t = n-1 .. 0).  fixed_small variance:
+    the model log-variance is posterior_log_variance_clipped, as is the true posterior's."""
+    n = len(tabs["betas"])
+    feats = speech_features(sd, wav)
+    flat = lambda z: z.mean(dim=list(range(1, z.dim())))  # noqa: E731
+    ln2 = float(np.log(2.0))
+    vb, x0_mse, mse = [], [], []
+    for k, t in enumerate(range(n - 1, -1, -1)):
+        noise = tape[k]
+        x_t = _f32(tabs["sqrt_alphas_cumprod"], t) * x_start + _f32(tabs["sqrt_one_minus_alphas_cumprod"], t) * noise
+        tt = torch.full((x_start.shape[0],), int(tabs["timestep_map"][t]), dtype=torch.long)
+        eps_model = denoiser(sd, model_type, heads, x_t, tt, feats)
+        a, b = _f32(tabs["sqrt_recip_alphas_cumprod"], t), _f32(tabs["sqrt_recipm1_alphas_cumprod"], t)
+        pred = a * x_t - b * eps_model
+        c1, c2 = _f32(tabs["posterior_mean_coef1"], t), _f32(tabs["posterior_mean_coef2"], t)
+        lv = _f32(tabs["posterior_log_variance_clipped"], t)
+        true_mean, mean = c1 * x_start + c2 * x_t, c1 * pred + c2 * x_t
+        kl = 0.5 * (-1.0 + lv - lv + torch.exp(lv - lv) + ((true_mean - mean) ** 2) * torch.exp(-lv))
+        centered = (x_start - mean) * torch.exp(-(0.5 * lv))
+        nll = -((-centered ** 2 / 2) - torch.log(torch.sqrt(2 * torch.tensor(math.pi))))
+        vb.append(flat(nll) / ln2 if t == 0 else flat(kl) / ln2)
+        x0_mse.append(flat((pred - x_start) ** 2))
+        mse.append(flat(((a * x_t - pred) / b - noise) ** 2))
+    vb, x0_mse, mse = torch.stack(vb, 1), torch.stack(x0_mse, 1), torch.stack(mse, 1)
+    qt_mean = _f32(tabs["sqrt_alphas_cumprod"], n - 1) * x_start
+    qt_lv = _f32(tabs["log_one_minus_alphas_cumprod"], n - 1)
+    prior = flat(0.5 * (-1.0 + 0.0 - qt_lv + torch.exp(qt_lv - 0.0) + (qt_mean ** 2) * 1.0)) / ln2
+    return {"total_bpd": vb.sum(1) + prior, "prior_bpd": prior, "x_start_mse": x0_mse, "vb": vb, "mse": mse}

@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 namespace gd {
 
@@ -50,6 +51,28 @@ int check_device() {
     }
     if (!ok) return set_error(GD_ERR_ARCH, "these kernels are built for sm_100a (B200) only");
     return GD_OK;
+}
+
+static bool pdl_enabled() {
+    const char* e = getenv("GD_PDL");
+    return !(e && e[0] == '0');
+}
+
+void fill_launch(LaunchCfg& L, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x) {
+    L.cfg = cudaLaunchConfig_t{};
+    L.cfg.gridDim = grid, L.cfg.blockDim = block, L.cfg.dynamicSmemBytes = smem, L.cfg.stream = stream;
+    int n = 0;
+    if (cluster_x > 1) {
+        L.attrs[n].id = cudaLaunchAttributeClusterDimension;
+        L.attrs[n].val.clusterDim.x = cluster_x, L.attrs[n].val.clusterDim.y = 1, L.attrs[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl_enabled()) {
+        L.attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        L.attrs[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    L.cfg.attrs = L.attrs, L.cfg.numAttrs = n;
 }
 
 int validate_ddpm(const gd_ddpm_desc* u) {

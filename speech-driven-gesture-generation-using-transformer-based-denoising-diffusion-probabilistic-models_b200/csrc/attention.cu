@@ -180,6 +180,8 @@ __global__ void __launch_bounds__(ATT_MAX_WARPS * 32, 3) dconv_attention_kernel(
         const float* b = which == 0 ? p.bq : (which == 1 ? p.bk : p.bv);
         s_taps[i] = j < DK * 3 ? __ldg(w + j) : __ldg(b + j - DK * 3);
     }
+    pdl_launch_dependents();
+    pdl_wait();  // the conv taps are weights; everything below reads the previous kernel's output
     __syncthreads();
     conv_stage<T, DK>(sq, p.Lq, Lq_pad, p.q, p.q_rows, p.q_ld, clip, head, s_taps, s_taps + DK * 3);
     conv_stage<T, DK>(sk, p.Lk, LK_PAD, p.k, p.kv_rows, p.kv_ld, clip, head, s_taps + DK * 4, s_taps + DK * 7);
@@ -297,7 +299,7 @@ static int launch_attention(const AttnParams& p, int n_clips, cudaStream_t s) {
         const int r4 = (tiles + 3) / 4, r5 = (tiles + 4) / 5;
         warps = (r5 * 5 - tiles < r4 * 4 - tiles) ? 5 : 4;
     }
-    dconv_attention_kernel<T, DK, KB><<<n_clips * p.heads, warps * 32, smem, s>>>(p);
+    GD_CUDA_CHECK(launch_k(dconv_attention_kernel<T, DK, KB>, n_clips * p.heads, warps * 32, smem, s, 1, p));
     count_launch();
     GD_CUDA_CHECK(cudaGetLastError());
     return GD_OK;
@@ -340,7 +342,8 @@ struct Attn2Geom {
     int n_items, groups;  // groups = heads / (64 / d_k)
     // byte offsets in dynamic smem.  Every raw tensor block is [zero row | L token rows | zero rows up to L_pad+1]:
     // the zero rows are the conv's "same" padding and are never written by the TMA engine
-    int raw_k_off, raw_v_off, raw_bytes, cv_q_off, cv_k_off, cv_v_off, taps_off, bar_off;
+    // raw_stages (1 or 2) such blocks: small items keep two loads in flight per CTA
+    int raw_k_off, raw_v_off, raw_stage_bytes, raw_stages, raw_bytes, cv_q_off, cv_k_off, cv_v_off, taps_off, bar_off;
     uint32_t tx_bytes;
 };
 
@@ -378,13 +381,10 @@ dconv_attention_tma_kernel(const __grid_constant__ CUtensorMap tm_q0, const __gr
     constexpr int HG = 64 / DK;       // heads per item
     constexpr int CPH = DK / 8;       // 16-B chunks per head row
     constexpr int LK_PAD = KB * 16;
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
     const int Lq = p.Lq, Lk = p.Lk;
     const int Lq_pad = (Lq + 15) & ~15;
-    uint8_t* raw_q = smem;
-    uint8_t* raw_k = smem + geo.raw_k_off;
-    uint8_t* raw_v = smem + geo.raw_v_off;
     uint8_t* cv_q = smem + geo.cv_q_off;
     uint8_t* cv_k = smem + geo.cv_k_off;
     uint8_t* cv_v = smem + geo.cv_v_off;
@@ -397,7 +397,8 @@ dconv_attention_tma_kernel(const __grid_constant__ CUtensorMap tm_q0, const __gr
         prefetch_tensormap(&tm_q0), prefetch_tensormap(&tm_k0), prefetch_tensormap(&tm_v0);
         if (p.q_rows[1]) prefetch_tensormap(&tm_q1);
         if (p.kv_rows[1]) prefetch_tensormap(&tm_k1), prefetch_tensormap(&tm_v1);
-        mbar_init(full_bar, 1);
+        mbar_init(&full_bar[0], 1);
+        mbar_init(&full_bar[1], 1);
         fence_barrier_init();
     }
     for (int i = tid; i < 3 * DK * 4; i += nthr) {
@@ -410,24 +411,33 @@ dconv_attention_tma_kernel(const __grid_constant__ CUtensorMap tm_q0, const __gr
     }
     for (int i = tid; i < geo.raw_bytes / 16; i += nthr) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();  // the zero fill is ordered before the TMA writes that follow the barrier
+    pdl_launch_dependents();
+    pdl_wait();  // set-up above touched only weights and shared memory; Q/K/V come from the previous kernel
     __syncthreads();
 
-    auto issue_load = [&](int item) {  // one thread; token rows start at raw row 1
+    auto issue_load = [&](int item, int stage) {  // one thread; token rows start at raw row 1 of the stage's blocks
         const int clip = item / geo.groups, col0 = (item % geo.groups) * 64;
-        mbar_arrive_expect_tx(full_bar, geo.tx_bytes);
-        tma_load_2d(raw_q + ATT2_ROW_BYTES, &tm_q0, full_bar, col0, clip * p.q_rows[0]);
-        if (p.q_rows[1]) tma_load_2d(raw_q + (1 + p.q_rows[0]) * ATT2_ROW_BYTES, &tm_q1, full_bar, col0, clip * p.q_rows[1]);
-        tma_load_2d(raw_k + ATT2_ROW_BYTES, &tm_k0, full_bar, col0, clip * p.kv_rows[0]);
-        tma_load_2d(raw_v + ATT2_ROW_BYTES, &tm_v0, full_bar, col0, clip * p.kv_rows[0]);
+        uint8_t* raw_q = smem + stage * geo.raw_stage_bytes;
+        uint8_t* raw_k = raw_q + geo.raw_k_off;
+        uint8_t* raw_v = raw_q + geo.raw_v_off;
+        uint64_t* bar = &full_bar[stage];
+        mbar_arrive_expect_tx(bar, geo.tx_bytes);
+        tma_load_2d(raw_q + ATT2_ROW_BYTES, &tm_q0, bar, col0, clip * p.q_rows[0]);
+        if (p.q_rows[1]) tma_load_2d(raw_q + (1 + p.q_rows[0]) * ATT2_ROW_BYTES, &tm_q1, bar, col0, clip * p.q_rows[1]);
+        tma_load_2d(raw_k + ATT2_ROW_BYTES, &tm_k0, bar, col0, clip * p.kv_rows[0]);
+        tma_load_2d(raw_v + ATT2_ROW_BYTES, &tm_v0, bar, col0, clip * p.kv_rows[0]);
         if (p.kv_rows[1]) {
-            tma_load_2d(raw_k + (1 + p.kv_rows[0]) * ATT2_ROW_BYTES, &tm_k1, full_bar, col0, clip * p.kv_rows[1]);
-            tma_load_2d(raw_v + (1 + p.kv_rows[0]) * ATT2_ROW_BYTES, &tm_v1, full_bar, col0, clip * p.kv_rows[1]);
+            tma_load_2d(raw_k + (1 + p.kv_rows[0]) * ATT2_ROW_BYTES, &tm_k1, bar, col0, clip * p.kv_rows[1]);
+            tma_load_2d(raw_v + (1 + p.kv_rows[0]) * ATT2_ROW_BYTES, &tm_v1, bar, col0, clip * p.kv_rows[1]);
         }
     };
 
     int item = blockIdx.x;
-    if (tid == 0 && item < geo.n_items) issue_load(item);
-    uint32_t phase = 0;
+    const int n_stages = geo.raw_stages;
+    if (tid == 0)
+        for (int st = 0; st < n_stages; ++st)
+            if (item + st * (int)gridDim.x < geo.n_items) issue_load(item + st * gridDim.x, st);
+    int k_iter = 0;
     const int g = lane >> 2, t = lane & 3;
     const int sw = lane & 7;  // every ldmatrix row index below is (multiple of 8) + (lane & 7)
     const int nsq = Lq_pad / 16, nsk = LK_PAD / 16;
@@ -439,10 +449,14 @@ dconv_attention_tma_kernel(const __grid_constant__ CUtensorMap tm_q0, const __gr
     const uint32_t vrow_u = smem_u32(cv_v) + ((lane & 7) + ((lane >> 3) & 1) * 8) * ATT2_ROW_BYTES;
     const float scale_log2 = p.scale_log2;
 
-    for (; item < geo.n_items; item += gridDim.x) {
+    for (; item < geo.n_items; item += gridDim.x, ++k_iter) {
         const int clip = item / geo.groups, grp = item % geo.groups;
-        mbar_wait(full_bar, phase);
-        phase ^= 1;
+        const int stage = n_stages == 2 ? (k_iter & 1) : 0;
+        const uint32_t phase = (n_stages == 2 ? (k_iter >> 1) : k_iter) & 1;
+        const uint8_t* raw_q = smem + stage * geo.raw_stage_bytes;
+        const uint8_t* raw_k = raw_q + geo.raw_k_off;
+        const uint8_t* raw_v = raw_q + geo.raw_v_off;
+        mbar_wait(&full_bar[stage], phase);
         // ---- depth-wise conv3 over tokens: raw -> cv, one unit = 16 tokens x 4 columns, no boundary predicates
         for (int it = tid; it < conv_items; it += nthr) {
             const int hc4 = it & 15, sg = it >> 4;  // 8-byte column group within the 128-B row, 16-row segment
@@ -453,7 +467,7 @@ dconv_attention_tma_kernel(const __grid_constant__ CUtensorMap tm_q0, const __gr
             conv_unit16(src, dst, hc4 >> 1, s_taps + which * DK * 4 + ((hc4 >> 1) % CPH) * 32 + (hc4 & 1) * 4);
         }
         __syncthreads();  // cv complete, raw free
-        if (tid == 0 && item + (int)gridDim.x < geo.n_items) issue_load(item + gridDim.x);
+        if (tid == 0 && item + n_stages * (int)gridDim.x < geo.n_items) issue_load(item + n_stages * gridDim.x, stage);
 
         // ---- attention core: one task = (head of the group, 16-query tile)
         for (int task = warp; task < HG * q_tiles; task += (nthr >> 5)) {
@@ -571,7 +585,13 @@ static int launch_attention_tma(const AttnParams& p, int n_clips, cudaStream_t s
     geo.n_items = n_clips * geo.groups;
     geo.raw_k_off = (Lq_pad + 2) * ATT2_ROW_BYTES;
     geo.raw_v_off = geo.raw_k_off + (Lk_pad + 2) * ATT2_ROW_BYTES;
-    geo.raw_bytes = geo.raw_v_off + (Lk_pad + 2) * ATT2_ROW_BYTES;
+    geo.raw_stage_bytes = geo.raw_v_off + (Lk_pad + 2) * ATT2_ROW_BYTES;
+    const int cv_bytes = (Lq_pad + 2 * Lk_pad) * ATT2_ROW_BYTES;
+    const int fixed_bytes = cv_bytes + 3 * DK * 4 * (int)sizeof(float) + 16 + 128;
+    // a second raw stage (two items in flight) whenever four CTAs per SM still fit: the small-item launches
+    // (34..40 tokens) are bound by the latency of their loads, not by shared-memory capacity
+    geo.raw_stages = (2 * geo.raw_stage_bytes + fixed_bytes <= 56 * 1024) ? 2 : 1;
+    geo.raw_bytes = geo.raw_stages * geo.raw_stage_bytes;
     geo.cv_q_off = geo.raw_bytes;
     geo.cv_k_off = geo.cv_q_off + Lq_pad * ATT2_ROW_BYTES;
     geo.cv_v_off = geo.cv_k_off + Lk_pad * ATT2_ROW_BYTES;
@@ -610,7 +630,7 @@ static int launch_attention_tma(const AttnParams& p, int n_clips, cudaStream_t s
     if (per_sm < 1) return set_error(GD_ERR_CUDA, "gd_dconv_attention: kernel does not fit on an SM (smem %zu B)", smem);
     int grid = per_sm * sm_count();
     if (grid > geo.n_items) grid = geo.n_items;
-    kern<<<grid, warps * 32, smem, s>>>(tq[0], tq[1], tk[0], tk[1], tv[0], tv[1], p, geo);
+    GD_CUDA_CHECK(launch_k(kern, grid, warps * 32, smem, s, 1, tq[0], tq[1], tk[0], tk[1], tv[0], tv[1], p, geo));
     count_launch();
     GD_CUDA_CHECK(cudaGetLastError());
     return GD_OK;

@@ -24,6 +24,14 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the library is launched with programmatic stream serialization: its CTAs may start (and run their
+// set-up: barrier init, TMEM allocation, tensor-map prefetch, weight-only preloads) while the previous kernel of the
+// stream is still draining.  pdl_wait() blocks until that kernel has completed and its writes are visible; it MUST
+// precede the first access to any buffer another kernel of the chain reads or writes.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+
 // ---------------------------------------------------------------- clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;

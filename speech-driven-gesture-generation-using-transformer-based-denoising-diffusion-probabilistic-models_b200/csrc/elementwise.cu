@@ -17,6 +17,8 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
                                                              const float* __restrict__ beta,
                                                              __nv_bfloat16* __restrict__ out, int ldo, int M,
                                                              float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int V = D / 128;  // float4 chunks per lane
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
@@ -55,6 +57,8 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
 // frame is the fastest index so x/noise/eps accesses are coalesced.
 __global__ void __launch_bounds__(256) ddpm_update_kernel(const gd_ddpm_desc u, const float* __restrict__ eps,
                                                           int c_span) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = *u.step_ptr;
     const DdpmStepCoefs cf = ddpm_load_coefs(u, t);
     const size_t total = (size_t)u.n_clips * c_span * u.T;
@@ -92,6 +96,8 @@ __global__ void __launch_bounds__(256) scatter_row_f32_kernel(float* __restrict_
                                                               const float* __restrict__ table,
                                                               const int* __restrict__ step_ptr, int n_clips,
                                                               int rows_per_clip, int row_index, int width, int ld) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = *step_ptr;
     const int w4 = width >> 2;
     const float4* trow = reinterpret_cast<const float4*>(table + (size_t)t * width);
@@ -118,6 +124,8 @@ __global__ void __launch_bounds__(256) scatter_row_bf16_kernel(__nv_bfloat16* __
                                                                const __nv_bfloat16* __restrict__ table,
                                                                const int* __restrict__ step_ptr, int n_clips,
                                                                int rows_per_clip, int row_index, int width, int ld) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = *step_ptr;
     const int w8 = width >> 3;
     const uint4* trow = reinterpret_cast<const uint4*>(table + (size_t)t * width);
@@ -133,6 +141,8 @@ __global__ void __launch_bounds__(256) scatter_row_bf16_kernel(__nv_bfloat16* __
 __global__ void __launch_bounds__(256) pack_pose_rows_kernel(const float* __restrict__ x,
                                                              __nv_bfloat16* __restrict__ xa, int n_clips, int C,
                                                              int T, int ld) {
+    pdl_launch_dependents();
+    pdl_wait();
     const size_t total = (size_t)n_clips * T * ld;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % ld);
@@ -146,6 +156,8 @@ __global__ void __launch_bounds__(256) pack_pose_rows_kernel(const float* __rest
 __global__ void __launch_bounds__(256) cast_rows_bf16_kernel(const float* __restrict__ src, int lds,
                                                              __nv_bfloat16* __restrict__ dst, int ldd, int rows,
                                                              int cols, int cols_padded) {
+    pdl_launch_dependents();
+    pdl_wait();
     const size_t total = (size_t)rows * cols_padded;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % cols_padded);
@@ -154,7 +166,11 @@ __global__ void __launch_bounds__(256) cast_rows_bf16_kernel(const float* __rest
     }
 }
 
-__global__ void step_add_kernel(int* step_ptr, int delta) { *step_ptr += delta; }
+__global__ void step_add_kernel(int* step_ptr, int delta) {
+    pdl_launch_dependents();
+    pdl_wait();
+    *step_ptr += delta;
+}
 
 static inline int grid_for(size_t total, int block) {
     size_t g = (total + block - 1) / block;
@@ -174,16 +190,17 @@ extern "C" int gd_layernorm(const float* x, int32_t ldx, const float* gamma, con
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const int wpb = 8, grid = (M + wpb - 1) / wpb;
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
-    if (D == 256)
-        layernorm_rows_kernel<256><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, o, ldo, M, eps);
-    else if (D == 512)
-        layernorm_rows_kernel<512><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, o, ldo, M, eps);
-    else if (D == 128)
-        layernorm_rows_kernel<128><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, o, ldo, M, eps);
-    else if (D == 1024)
-        layernorm_rows_kernel<1024><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, o, ldo, M, eps);
-    else
+    if (D == 256) {
+        GD_CUDA_CHECK(launch_k(layernorm_rows_kernel<256>, grid, wpb * 32, 0, s, 1, x, ldx, gamma, beta, o, ldo, M, eps));
+    } else if (D == 512) {
+        GD_CUDA_CHECK(launch_k(layernorm_rows_kernel<512>, grid, wpb * 32, 0, s, 1, x, ldx, gamma, beta, o, ldo, M, eps));
+    } else if (D == 128) {
+        GD_CUDA_CHECK(launch_k(layernorm_rows_kernel<128>, grid, wpb * 32, 0, s, 1, x, ldx, gamma, beta, o, ldo, M, eps));
+    } else if (D == 1024) {
+        GD_CUDA_CHECK(launch_k(layernorm_rows_kernel<1024>, grid, wpb * 32, 0, s, 1, x, ldx, gamma, beta, o, ldo, M, eps));
+    } else {
         return set_error(GD_ERR_INVALID, "gd_layernorm: D=%d unsupported (128/256/512/1024)", D);
+    }
     count_launch();
     GD_CUDA_CHECK(cudaGetLastError());
     return GD_OK;
@@ -199,7 +216,7 @@ extern "C" int gd_ddpm_update(const gd_ddpm_desc* u, const float* eps, void* str
         c_span = u->ld_xa;
     }
     const size_t total = (size_t)u->n_clips * c_span * u->T;
-    ddpm_update_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*u, eps, c_span);
+    GD_CUDA_CHECK(launch_k(ddpm_update_kernel, grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), 1, *u, eps, c_span));
     count_launch();
     GD_CUDA_CHECK(cudaGetLastError());
     return GD_OK;
@@ -212,8 +229,8 @@ extern "C" int gd_scatter_step_row_f32(float* dst, const float* init, const floa
     if (width % 4 || ld % 4 || ld < width || row_index < 0 || row_index >= rows_per_clip || n_clips <= 0)
         return set_error(GD_ERR_INVALID, "gd_scatter_step_row_f32: bad shape");
     const size_t total = init ? (size_t)n_clips * rows_per_clip * (width / 4) : (size_t)n_clips * (width / 4);
-    scatter_row_f32_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        dst, init, table, step_ptr, n_clips, rows_per_clip, row_index, width, ld);
+    GD_CUDA_CHECK(launch_k(scatter_row_f32_kernel, grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), 1, dst,
+                           init, table, step_ptr, n_clips, rows_per_clip, row_index, width, ld));
     count_launch();
     GD_CUDA_CHECK(cudaGetLastError());
     return GD_OK;
@@ -226,9 +243,9 @@ extern "C" int gd_scatter_step_row_bf16(void* dst, const void* table, const int3
     if (width % 8 || ld % 8 || ld < width || row_index < 0 || row_index >= rows_per_clip || n_clips <= 0)
         return set_error(GD_ERR_INVALID, "gd_scatter_step_row_bf16: bad shape");
     const size_t total = (size_t)n_clips * (width / 8);
-    scatter_row_bf16_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<__nv_bfloat16*>(dst), reinterpret_cast<const __nv_bfloat16*>(table), step_ptr, n_clips,
-        rows_per_clip, row_index, width, ld);
+    GD_CUDA_CHECK(launch_k(scatter_row_bf16_kernel, grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), 1,
+                           reinterpret_cast<__nv_bfloat16*>(dst), reinterpret_cast<const __nv_bfloat16*>(table), step_ptr,
+                           n_clips, rows_per_clip, row_index, width, ld));
     count_launch();
     GD_CUDA_CHECK(cudaGetLastError());
     return GD_OK;
@@ -239,8 +256,8 @@ extern "C" int gd_pack_pose_rows(const float* x, void* xa_bf16, int32_t n_clips,
     if (!x || !xa_bf16 || n_clips <= 0 || C <= 0 || T <= 0 || ld < C)
         return set_error(GD_ERR_INVALID, "gd_pack_pose_rows: bad argument");
     const size_t total = (size_t)n_clips * T * ld;
-    pack_pose_rows_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        x, reinterpret_cast<__nv_bfloat16*>(xa_bf16), n_clips, C, T, ld);
+    GD_CUDA_CHECK(launch_k(pack_pose_rows_kernel, grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), 1, x,
+                           reinterpret_cast<__nv_bfloat16*>(xa_bf16), n_clips, C, T, ld));
     count_launch();
     GD_CUDA_CHECK(cudaGetLastError());
     return GD_OK;
@@ -251,8 +268,8 @@ extern "C" int gd_cast_rows_bf16(const float* src, int32_t lds, void* dst, int32
     if (!src || !dst || rows <= 0 || cols <= 0 || cols_padded < cols || ldd < cols_padded || lds < cols)
         return set_error(GD_ERR_INVALID, "gd_cast_rows_bf16: bad argument");
     const size_t total = (size_t)rows * cols_padded;
-    cast_rows_bf16_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, rows, cols, cols_padded);
+    GD_CUDA_CHECK(launch_k(cast_rows_bf16_kernel, grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), 1, src,
+                           lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, rows, cols, cols_padded));
     count_launch();
     GD_CUDA_CHECK(cudaGetLastError());
     return GD_OK;
@@ -260,7 +277,7 @@ extern "C" int gd_cast_rows_bf16(const float* src, int32_t lds, void* dst, int32
 
 extern "C" int gd_step_add(int32_t* step_ptr, int32_t delta, void* stream) {
     if (!step_ptr) return set_error(GD_ERR_INVALID, "gd_step_add: null pointer");
-    step_add_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(step_ptr, delta);
+    GD_CUDA_CHECK(launch_k(step_add_kernel, 1, 1, 0, reinterpret_cast<cudaStream_t>(stream), 1, step_ptr, delta));
     count_launch();
     GD_CUDA_CHECK(cudaGetLastError());
     return GD_OK;

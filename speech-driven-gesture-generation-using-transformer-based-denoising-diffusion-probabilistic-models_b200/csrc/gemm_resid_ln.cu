@@ -134,6 +134,8 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     __syncthreads();
     if (NSPLIT > 1) cluster_sync_all();  // the peer's barriers exist before anything is sent to them
     tc_fence_after_sync();
+    pdl_launch_dependents();
+    pdl_wait();  // bias/gamma/beta above are weights; A, H and xn belong to the chain
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
@@ -414,14 +416,7 @@ static int launch_resid_ln(const gd_linear_desc* d, const gd_ln_desc* ln, cudaSt
     const int m_tiles = (d->M + RL_BLOCK_M - 1) / RL_BLOCK_M;
     const int max_clusters = sm_count() / NSPLIT;
     const int grid = (m_tiles < max_clusters ? m_tiles : max_clusters) * NSPLIT;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(RL_THREADS);
-    cfg.dynamicSmemBytes = RL_SMEM_BYTES, cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = NSPLIT, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr, cfg.numAttrs = 1;
-    GD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_resid_ln_kernel<NSPLIT>, ta, tb, th, tx, tpf, p));
+    GD_CUDA_CHECK(launch_k(gemm_resid_ln_kernel<NSPLIT>, grid, RL_THREADS, RL_SMEM_BYTES, stream, NSPLIT, ta, tb, th, tx, tpf, p));
     count_launch();
     GD_CUDA_CHECK(cudaGetLastError());
     return GD_OK;

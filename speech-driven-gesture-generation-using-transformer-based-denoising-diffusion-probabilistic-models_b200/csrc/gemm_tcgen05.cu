@@ -135,58 +135,71 @@ __device__ __forceinline__ void epilogue_direct_chunk(const GemmParams& p, int r
     }
 }
 
-// DDPM epilogue: row = clip*T + frame, columns = pose channels.  Lanes of a warp hold consecutive
-// frames, so for a fixed channel the (N,C,T) accesses of a warp are contiguous.
-__device__ __forceinline__ void epilogue_ddpm_chunk(const GemmParams& p, const DdpmStepCoefs& cf, int t, int row,
-                                                    int col0, uint32_t (&v)[32]) {
+// DDPM epilogue: row = clip*T + frame, columns = pose channels.  Lanes of a warp hold consecutive frames, so for a fixed
+// channel the (N,C,T) accesses of a warp are contiguous.  x, the noise slab of this step and the optional eps/x0
+// outputs share one 32-bit element offset per column (off0 + j*T); AUX / INPAINT are compile-time so the common
+// sampling step carries no dead predicates (the first version spent ~94 instructions per element, mostly on 64-bit
+// index arithmetic and per-element pointer tests).
+template <bool AUX, bool INPAINT>
+__device__ __forceinline__ void epilogue_ddpm_chunk(const GemmParams& p, const DdpmStepCoefs& cf, const float* tape_t,
+                                                    int row, int col0, const uint32_t (&v)[32]) {
     const gd_ddpm_desc& u = p.ddpm;
-    const int clip = row / u.T;
-    const int frame = row - clip * u.T;
-    const size_t clip_base = (size_t)clip * u.C * u.T + frame;
-    const size_t tape_base = (size_t)t * u.n_clips * u.C * u.T;
-    const bool inpaint = u.inpaint_seed != nullptr;
+    const int T = u.T;
+    const int clip = row / T;
+    const int frame = row - clip * T;
+    const uint32_t off0 = static_cast<uint32_t>((clip * u.C + col0) * T + frame);
+    const int ncol = u.C - col0;  // columns >= ncol of this chunk are padding (warp-uniform)
+    float* const xp = u.x + off0;
+    const float* const zp = tape_t ? tape_t + off0 : nullptr;
+    float* const eps_o = (AUX && u.eps_out) ? u.eps_out + off0 : nullptr;
+    float* const x0_o = (AUX && u.x0_out) ? u.x0_out + off0 : nullptr;
     float m = 0.f, f = 0.f;
-    if (inpaint) {
-        m = __ldg(u.inpaint_mask + (size_t)clip * u.T + frame);
+    const float* sp = nullptr;
+    if (INPAINT) {
+        m = __ldg(u.inpaint_mask + clip * T + frame);
         f = __ldg(u.inpaint_factor + frame);
+        sp = u.inpaint_seed + (static_cast<size_t>(clip) * T + frame) * u.C + col0;
     }
-    // all loads of the chunk first (x may alias the stores below, so the compiler cannot hoist them itself)
-    float xv[32], zv[32], sv[32];
+    // per 16-column half: all loads first (x aliases the stores below, so the compiler cannot hoist them itself)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const int c = col0 + j;
-        const size_t idx = clip_base + (size_t)c * u.T;
-        const bool ok = c < u.C;
-        xv[j] = ok ? u.x[idx] : 0.f;
-        zv[j] = (ok && u.noise_tape) ? __ldg(u.noise_tape + tape_base + idx) : 0.f;
-        sv[j] = (ok && inpaint) ? __ldg(u.inpaint_seed + ((size_t)clip * u.T + frame) * u.C + c) : 0.f;
-    }
-    float xn[32];
+    for (int h = 0; h < 2; ++h) {
+        float xv[16], zv[16];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const int c = col0 + j;
-        xn[j] = 0.0f;
-        if (c < u.C) {
-            const size_t idx = clip_base + (size_t)c * u.T;
-            const float eps = __uint_as_float(v[j]) + __ldg(p.bias + c);
-            float x0;
-            const float xnext = ddpm_update_elem(cf, xv[j], eps, zv[j], inpaint, sv[j], m, f, u.clip_x0, &x0);
-            u.x[idx] = xnext;
-            if (u.eps_out) u.eps_out[idx] = eps;
-            if (u.x0_out) u.x0_out[idx] = x0;
-            xn[j] = xnext;
+        for (int i = 0; i < 16; ++i) {
+            const int j = h * 16 + i;
+            const bool ok = j < ncol;
+            xv[i] = ok ? xp[j * T] : 0.f;
+            zv[i] = (ok && zp) ? __ldg(zp + j * T) : 0.f;
         }
-    }
-    if (u.xa_bf16) {
-        uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(u.xa_bf16) + (size_t)row * u.ld_xa + col0);
+        float xn[16];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint4 w;
-            w.x = pack_bf16x2(xn[8 * j + 0], xn[8 * j + 1]);
-            w.y = pack_bf16x2(xn[8 * j + 2], xn[8 * j + 3]);
-            w.z = pack_bf16x2(xn[8 * j + 4], xn[8 * j + 5]);
-            w.w = pack_bf16x2(xn[8 * j + 6], xn[8 * j + 7]);
-            o4[j] = w;
+        for (int i = 0; i < 16; ++i) {
+            const int j = h * 16 + i;
+            xn[i] = 0.0f;
+            if (j < ncol) {
+                const float eps = __uint_as_float(v[j]) + __ldg(p.bias + col0 + j);
+                const float sv = INPAINT ? __ldg(sp + j) : 0.f;
+                float x0;
+                const float xnext = ddpm_update_elem(cf, xv[i], eps, zv[i], INPAINT, sv, m, f, u.clip_x0, &x0);
+                xp[j * T] = xnext;
+                if (AUX) {
+                    if (eps_o) eps_o[j * T] = eps;
+                    if (x0_o) x0_o[j * T] = x0;
+                }
+                xn[i] = xnext;
+            }
+        }
+        if (u.xa_bf16) {
+            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(u.xa_bf16) + (size_t)row * u.ld_xa + col0 + h * 16);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                uint4 w;
+                w.x = pack_bf16x2(xn[8 * j + 0], xn[8 * j + 1]);
+                w.y = pack_bf16x2(xn[8 * j + 2], xn[8 * j + 3]);
+                w.z = pack_bf16x2(xn[8 * j + 4], xn[8 * j + 5]);
+                w.w = pack_bf16x2(xn[8 * j + 6], xn[8 * j + 7]);
+                o4[j] = w;
+            }
         }
     }
 }
@@ -251,6 +264,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     __syncthreads();
     if (CL > 1) cluster_sync_all();  // the peer's barriers and TMEM exist before any cross-CTA traffic
     tc_fence_after_sync();
+    pdl_launch_dependents();
+    pdl_wait();  // operands and outputs belong to the chain: nothing below may run before the previous kernel is done
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
@@ -329,9 +344,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         constexpr int WCOLS = BN / 2;
         int t = 0;
         DdpmStepCoefs cf;
+        const float* tape_t = nullptr;
+        bool ddpm_aux = false, ddpm_inpaint = false;
         if (MODE == MODE_DDPM) {
             t = *p.ddpm.step_ptr;
             cf = ddpm_load_coefs(p.ddpm, t);
+            if (p.ddpm.noise_tape) tape_t = p.ddpm.noise_tape + (size_t)t * p.ddpm.n_clips * p.ddpm.C * p.ddpm.T;
+            ddpm_aux = p.ddpm.eps_out != nullptr || p.ddpm.x0_out != nullptr;
+            ddpm_inpaint = p.ddpm.inpaint_seed != nullptr;
         }
         uint8_t* stg_base = staging + ew * Cfg::STAGING_PER_WARP;
         constexpr int STG_CHUNK = (MODE == MODE_TMA_F32) ? 4096 : 2048;
@@ -409,9 +429,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 } else {
                     tmem_ld_wait();
                     if (row < p.M) {
-                        if (MODE == MODE_DDPM)
-                            epilogue_ddpm_chunk(p, cf, t, row, col0, v);
-                        else
+                        if (MODE == MODE_DDPM) {
+                            if (ddpm_inpaint)
+                                epilogue_ddpm_chunk<true, true>(p, cf, tape_t, row, col0, v);
+                            else if (ddpm_aux)
+                                epilogue_ddpm_chunk<true, false>(p, cf, tape_t, row, col0, v);
+                            else
+                                epilogue_ddpm_chunk<false, false>(p, cf, tape_t, row, col0, v);
+                        } else
                             epilogue_direct_chunk(p, row, col0, v);
                     }
                 }
@@ -486,14 +511,7 @@ static int launch_gemm_cl(const GemmParams& p, const void* A, int lda, const voi
     const int work = ((m_tiles + CL - 1) / CL) * (p.N / BN);  // cluster-level work items
     const int max_clusters = sm_count() / CL;
     const int grid = (work < max_clusters ? work : max_clusters) * CL;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES, cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr, cfg.numAttrs = 1;
-    GD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BN, MODE, CL>, ta, tb, tout, p));
+    GD_CUDA_CHECK(launch_k(gemm_bf16_tn_kernel<BN, MODE, CL>, grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream, CL, ta, tb, tout, p));
     count_launch();
     GD_CUDA_CHECK(cudaGetLastError());
     return GD_OK;
@@ -585,6 +603,8 @@ extern "C" int gd_linear_ddpm(const gd_linear_desc* d, const gd_ddpm_desc* u, vo
     if (d->N != 128 || u->C > 128) return set_error(GD_ERR_INVALID, "gd_linear_ddpm: N must be 128 (padded d_pose)");
     if (d->M != u->n_clips * u->T) return set_error(GD_ERR_INVALID, "gd_linear_ddpm: M != n_clips*T");
     if (!d->bias) return set_error(GD_ERR_INVALID, "gd_linear_ddpm: bias required");
+    if ((int64_t)u->n_clips * u->C * u->T >= (int64_t)1 << 31)
+        return set_error(GD_ERR_INVALID, "gd_linear_ddpm: n_clips*C*T must stay below 2^31 elements");
     if (u->xa_bf16 && (u->ld_xa % 8 || u->ld_xa < 128))
         return set_error(GD_ERR_INVALID, "gd_linear_ddpm: ld_xa must be >= 128 and a multiple of 8");
     rc = check_device();

@@ -20,6 +20,22 @@ int validate_ddpm(const gd_ddpm_desc* u);
 int make_tmap_2d(CUtensorMap* m, CUtensorMapDataType dt, int elt_bytes, const void* base, uint64_t rows, uint64_t cols,
                  uint64_t ld_elems, uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swz);
 
+// Launch configuration with the library-wide attributes: optional cluster width and programmatic stream serialization
+// (GD_PDL=0 in the environment turns the latter off).
+struct LaunchCfg {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attrs[2];
+};
+void fill_launch(LaunchCfg& L, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x = 1);
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                            Args&&... args) {
+    LaunchCfg L;
+    fill_launch(L, grid, block, smem, stream, cluster_x);
+    return cudaLaunchKernelEx(&L.cfg, kern, static_cast<Args&&>(args)...);
+}
+
 #define GD_CUDA_CHECK(expr)                                                                          \
     do {                                                                                             \
         cudaError_t _e = (expr);                                                                     \

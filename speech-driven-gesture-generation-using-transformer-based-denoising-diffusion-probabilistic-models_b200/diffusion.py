@@ -185,6 +185,58 @@ class GaussianSpacedDiffusion(GaussianDiffusion):
         return self._run("ddim", model, shape, noise, denoise_fn, model_kwargs, device, progress, None, True)
 
 
+    # ------------------------------------------------------------------ variational bound (gaussian_diffusion.py:571-678)
+    @th.no_grad()
+    def calc_bpd_loop(self, model, x_start, model_kwargs, noise_tape=None):
+        """Variational lower bound in bits/dim, term by term (`calc_bpd_loop` :635-678, `_vb_terms_bpd` :571-610,
+        `_prior_bpd` :612-633).  Every timestep is an independent denoiser call on x_t = q_sample(x_start, t, noise)
+        (:182-205): the engine's step is teacher-forced with x_t and its fused final-projection epilogue hands back
+        pred_x_start; the bound terms are elementwise maps and one mean per clip, done with the reference's own op
+        order in fp32.  `noise_tape` (n_steps, N, C, T) in loop order replaces the per-step randn_like draws."""
+        from .engine import chain_for  # local import: the engine needs the CUDA library
+        device = x_start.device
+        x_start = x_start.float().contiguous()
+        shape = tuple(x_start.shape)
+        wav = (model_kwargs or {}).get("wav")
+        if wav is None:
+            raise ValueError("model_kwargs['wav'] is required")
+        chain = chain_for(model, self, shape, "ddpm", device)
+        chain.begin(th.zeros(shape, device=device), wav.to(device), need_tape=False)
+        n = self.num_timesteps
+        tab = lambda a: th.from_numpy(a).to(device).float()  # noqa: E731  (float64 table -> fp32 at gather, :691)
+        sa, s1a = tab(self.sqrt_alphas_cumprod), tab(self.sqrt_one_minus_alphas_cumprod)
+        c1, c2 = tab(self.posterior_mean_coef1), tab(self.posterior_mean_coef2)
+        lv = tab(self.posterior_log_variance_clipped)
+        ra, rm1 = tab(self.sqrt_recip_alphas_cumprod), tab(self.sqrt_recipm1_alphas_cumprod)
+        flat = lambda z: z.mean(dim=list(range(1, z.dim())))  # noqa: E731
+        ln2 = float(np.log(2.0))
+        vb, x_start_mse, mse = [], [], []
+        for k, t in enumerate(range(n - 1, -1, -1)):
+            noise = noise_tape[k].to(device).float() if noise_tape is not None else th.randn_like(x_start)
+            x_t = sa[t] * x_start + s1a[t] * noise
+            chain.set_state(x_t, t)
+            chain.step_eager()
+            pred = chain.x0.clone()  # pred_x_start of p_mean_variance
+            true_mean = c1[t] * x_start + c2[t] * x_t
+            mean = c1[t] * pred + c2[t] * x_t
+            kl = 0.5 * (-1.0 + lv[t] - lv[t] + th.exp(lv[t] - lv[t]) + ((true_mean - mean) ** 2) * th.exp(-lv[t]))
+            kl = flat(kl) / ln2
+            centered = (x_start - mean) * th.exp(-(0.5 * lv[t]))
+            log_probs = (-centered ** 2 / 2) - th.log(th.sqrt(2 * th.tensor(math.pi, device=device)))
+            decoder_nll = flat(-log_probs) / ln2
+            vb.append(decoder_nll if t == 0 else kl)
+            x_start_mse.append(flat((pred - x_start) ** 2))
+            eps = (ra[t] * x_t - pred) / rm1[t]
+            mse.append(flat((eps - noise) ** 2))
+        vb, x_start_mse, mse = th.stack(vb, dim=1), th.stack(x_start_mse, dim=1), th.stack(mse, dim=1)
+        qt_mean = sa[n - 1] * x_start
+        qt_logvar = tab(self.log_one_minus_alphas_cumprod)[n - 1]
+        kl_prior = 0.5 * (-1.0 + 0.0 - qt_logvar + th.exp(qt_logvar - 0.0) + ((qt_mean - 0.0) ** 2) * math.exp(-0.0))
+        prior_bpd = flat(kl_prior) / ln2
+        return {"total_bpd": vb.sum(dim=1) + prior_bpd, "prior_bpd": prior_bpd, "x_start_mse": x_start_mse, "vb": vb,
+                "mse": mse}
+
+
 def create_diffusion(diffusion_params, is_training):
     """model_creation.py:30-48."""
     if diffusion_params.type != "gaussian":

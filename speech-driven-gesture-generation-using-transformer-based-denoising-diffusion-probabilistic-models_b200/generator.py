@@ -133,8 +133,13 @@ class Generator:
             timings[rep] = start.elapsed_time(end)
         return np.sum(timings) / repetitions, np.std(timings)
 
-    def eval_bpd(self, poses, wavs, pose_seed_len=None):
-        raise NotImplementedError("variational-bound evaluation (calc_bpd_loop) is listed as a follow-up (SURVEY §8 f4)")
+    @th.no_grad()
+    def eval_bpd(self, poses: th.Tensor, wavs: th.Tensor, pose_seed_len: int = None, noise_tape: th.Tensor = None):
+        """generator.py:197-216: variational bound of `poses` (N,T,C) given `wavs`, on the device the model lives on.
+        (The `inpaint` model variant that needs pose_seed_len is not one of the shipped configs and is not built.)"""
+        device = next(self.model.parameters()).device
+        return self.diffusion.calc_bpd_loop(self.model, x_start=poses.to(device).transpose(1, 2),  # -> (N,C,T)
+                                            model_kwargs={"wav": wavs.to(device)}, noise_tape=noise_tape)
 
     @staticmethod
     def tensor2dtype(x: th.Tensor, dtype: str):

@@ -179,6 +179,32 @@ def sequence():
     print("sequence written", {k: v.shape for k, v in out.items()})
 
 
+def bpd():
+    """Variational bound through the reference's Generator.eval_bpd (generator.py:197-216 -> calc_bpd_loop): beat-ours,
+    20-step respaced process, boosted weights, fixed poses / speech / per-step noise."""
+    mp, d_pose, T, L = ref_params("beat", "ddim20")
+    th.manual_seed(0)
+    model, diffusion, *_ = create_model(d_pose=d_pose, model_params=mp, is_training=False)
+    model.eval()
+    model.load_state_dict(boosted_state_dict(model.state_dict(), seed=1))
+    gen = Generator(model, diffusion)
+    n = 2
+    wav = synthetic_wav(n, L, seed=51)
+    g = th.Generator().manual_seed(52)
+    poses = th.randn(n, T, d_pose, generator=g)
+    tape = [th.randn(n, d_pose, T, generator=g) for _ in range(diffusion.num_timesteps)]
+    it = iter(tape)
+    real = th.randn_like
+    th.randn_like = lambda x: next(it)
+    try:
+        res = gen.eval_bpd(poses, wav)
+    finally:
+        th.randn_like = real
+    out = {k: v.numpy() for k, v in res.items()}
+    np.savez_compressed(os.path.join(HERE, "beat_bpd_golden.npz"), **out)
+    print("bpd written", {k: v.shape for k, v in out.items()}, out["total_bpd"])
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     th.set_num_threads(8)
@@ -190,3 +216,5 @@ if __name__ == "__main__":
         config("tedexp")
     if what in ("sequence", "all"):
         sequence()
+    if what in ("bpd", "all"):
+        bpd()

@@ -97,6 +97,26 @@ def test_short_respaced_chain_vs_oracle(name, alg):
     assert th.equal(out, out2)
 
 
+@pytest.mark.parametrize("name", ["beat", "tedexp"])
+def test_fused_layernorm_plan_matches_two_kernel_plan(name):
+    """The optional plan with every LayerNorm fused into the residual GEMM in front of it (gd_linear_resid_ln, clusters of
+    two CTAs for d=512) against the default plan: same 20-step chain, same inputs."""
+    from gesture_b200.generator import Generator
+    N = 3
+    model, diffusion, C, T, L, params = build(name, "boost", respacing="ddim20", device="cuda")
+    wav = synthetic_wav(N, L, seed=22)
+    x_T, tape = noise_tape((N, C, T), 20, seed=9)
+    gen = Generator(model, diffusion)
+    outs = []
+    for fuse in (False, True):
+        model.fuse_layernorm = fuse
+        outs.append(gen.generate_sample((N, C, T), wav, noise=x_T, sample_alg="ddpm", device="cuda", progress=False,
+                                        noise_tape=tape).clone())
+    model.fuse_layernorm = False
+    err = rel_l2(outs[1], outs[0])
+    assert err < 5e-3, f"{name}: fused vs two-kernel plan rel-L2 {err:.3e}"
+
+
 def test_long_form_beat_4x_length():
     """BASELINE config 5: the beat model at 4x the config's sequence length (T=160, wav 128 000 -> 127 memory tokens):
     160-query / 127- and 160-key attention tiles, same weights."""

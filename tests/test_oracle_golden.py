@@ -162,3 +162,19 @@ def test_oracle_respaced_and_inpaint_chains():
     out = orc.sample_chain(sd, params.type, heads, tabs, x50, wav, None, alg="ddim",
                            blend=lambda x0: orc.inpaint_blend(x0, seedp, masks, 0))
     assert rel_l2(out.transpose(1, 2), g["boost.ddim50_inpaint.final"]) < 1e-3
+
+
+def test_oracle_bpd_terms():
+    """Variational-bound terms (calc_bpd_loop) of the oracle vs the reference's Generator.eval_bpd: beat, ddim20 process."""
+    import numpy as np
+    from util import GOLDEN
+    g = np.load(f"{GOLDEN}/beat_bpd_golden.npz")
+    model, diffusion, C, T, L, params = build("beat", "boost", respacing="ddim20")
+    tabs = orc.spaced_diffusion_tables("linear", 1000, "ddim20")
+    wav = synthetic_wav(2, L, seed=51)
+    rg = th.Generator().manual_seed(52)
+    poses = th.randn(2, T, C, generator=rg)
+    tape = [th.randn(2, C, T, generator=rg) for _ in range(20)]
+    out = orc.bpd_loop(model.state_dict(), params.type, params.Decoder.heads, tabs, poses.transpose(1, 2), wav, tape)
+    for k in ("total_bpd", "prior_bpd", "x_start_mse", "vb", "mse"):
+        assert rel_l2(out[k], g[k]) < 1e-3, k

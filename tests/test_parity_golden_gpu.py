@@ -111,3 +111,22 @@ def test_generate_sequence_vs_reference(monkeypatch):
         err = rel_l2(out, g[f"smooth{int(smooth)}"])
         print(f"[beat] generate_sequence smooth={smooth}: rel-L2 {err:.3e}")
         assert err < 2e-2, err
+
+
+def test_eval_bpd_vs_reference():
+    """Generator.eval_bpd (calc_bpd_loop over the engine's teacher-forced steps) vs the reference's output on the same
+    poses / speech / noise: beat, ddim20 process, boosted weights."""
+    import numpy as np
+    from gesture_b200.generator import Generator
+    from util import GOLDEN
+    g = np.load(f"{GOLDEN}/beat_bpd_golden.npz")
+    model, diffusion, C, T, L, params = build("beat", "boost", respacing="ddim20", device="cuda")
+    wav = synthetic_wav(2, L, seed=51)
+    rg = th.Generator().manual_seed(52)
+    poses = th.randn(2, T, C, generator=rg)
+    tape = th.stack([th.randn(2, C, T, generator=rg) for _ in range(20)])
+    out = Generator(model, diffusion).eval_bpd(poses, wav, noise_tape=tape)
+    for k in ("total_bpd", "prior_bpd", "x_start_mse", "vb", "mse"):
+        err = rel_l2(out[k], g[k])
+        print(f"[beat] eval_bpd {k}: rel-L2 {err:.3e}")
+        assert err < 2e-2, (k, err)
