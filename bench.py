@@ -22,6 +22,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+
+def workload_preset(name):
+    """-> (params, d_pose, frames, wav_len, default clips per GPU) of a bench workload."""
+    from gesture_b200.presets import preset
+    if name == "beat-ours-4x":
+        params, C, T, L = preset("beat-ours")
+        return params, C, 4 * T, 4 * L, 64
+    params, C, T, L = preset(name)
+    return params, C, T, L, (256 if name == "tedexp-ours" else 1024)
+
 import torch as th  # noqa: E402
 
 METRIC = "generated gesture frames/sec, full 1000-step DDPM chain"
@@ -34,8 +44,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="tedexp-ours", choices=["tedexp-ours", "beat-ours"])
-    ap.add_argument("--clips", type=int, default=None, help="clips per GPU (default 256 tedexp / 1024 beat)")
+    ap.add_argument("--workload", default="tedexp-ours", choices=["tedexp-ours", "beat-ours", "beat-ours-4x"],
+                    help="beat-ours-4x = BASELINE config 5: the beat model at 4x its window (160 frames, 8 s of speech)")
+    ap.add_argument("--clips", type=int, default=None, help="clips per GPU (default 256 tedexp / 1024 beat / 64 beat-4x)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32act"])
     ap.add_argument("--graph-steps", type=int, default=10, help="denoise steps captured per CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -108,7 +119,7 @@ class CpuReference:
         # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can
         th.set_num_threads(threads or os.cpu_count() or 1)
         self.orc = orc
-        self.params, self.C, self.T, L = preset(workload)
+        self.params, self.C, self.T, L, _ = workload_preset(workload)
         th.manual_seed(0)
         model, _, *_ = create_model(self.C, self.params)  # parameter container only; the oracle does the arithmetic
         self.sd = dict(model.state_dict())
@@ -198,8 +209,8 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
-    params, C, T, L = preset(args.workload)
-    clips = args.clips or (256 if args.workload == "tedexp-ours" else 1024)
+    params, C, T, L, default_clips = workload_preset(args.workload)
+    clips = args.clips or default_clips
     th.manual_seed(0)
     model, diffusion, *_ = create_model(C, params)  # random-init weights (seed 0), as BASELINE.json prescribes
     model.eval().to(dev)
