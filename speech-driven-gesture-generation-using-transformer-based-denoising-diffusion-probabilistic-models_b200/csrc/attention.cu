@@ -9,24 +9,13 @@
 // All K/V of a head fit in shared memory (<= 160 keys), so this is single-pass: no running-max rescale.
 // The token sequence of a clip is the concatenation of up to two row segments; the conv runs across the seam
 // (tedexp joint attention over [x ; memory], nn.py:105-113) and zero-pads only at the sequence ends.
-#include "common.cuh"
-#include "host_util.h"
+#include "attention_common.cuh"
 #include <cstdlib>
 
 namespace gd {
 
 constexpr int ATT_MAX_WARPS = 5;  // 4 or 5 warps per CTA (chosen per launch), several CTAs per SM
 
-struct AttnParams {
-    const void* q[2];
-    const void* k[2];
-    const void* v[2];
-    __nv_bfloat16* out[2];
-    int q_rows[2], q_ld[2], kv_rows[2], kv_ld[2], out_ld[2];
-    const float *wq, *bq, *wk, *bk, *wv, *bv;
-    int heads, Lq, Lk;
-    float scale_log2;  // d_k^-1/2 * log2(e)
-};
 
 // Raw (pre-conv) storage of 8 consecutive elements of a projected row: one 16-B load for bf16, two for fp32.
 // Loads go through the non-coherent path (ld.global.nc) so the compiler may batch them ahead of the smem stores.
@@ -133,15 +122,6 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float (&f)[8]) {
         f[2 * i] = __uint_as_float(w[i] << 16);
         f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
     }
-}
-__device__ __forceinline__ float4 unpack_bf16x4(const uint2& u) {
-    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
-                       __uint_as_float(u.y & 0xffff0000u));
-}
-__device__ __forceinline__ float ex2_approx(float x) {  // MUFU.EX2; -inf -> 0, which is what masked keys need
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
-    return y;
 }
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
@@ -559,7 +539,7 @@ dconv_attention_tma_kernel(const __grid_constant__ CUtensorMap tm_q0, const __gr
     }
 }
 
-static int make_rows_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+int make_rows_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
     static PFN_encodeTiled encode = get_encode_tiled();
     if (!encode) return set_error(GD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     cuuint64_t dims[2] = {cols, rows};
@@ -653,13 +633,13 @@ static int dispatch_kb_tma(const AttnParams& p, int n_clips, cudaStream_t s) {
     return set_error(GD_ERR_INVALID, "gd_dconv_attention: need 0 < keys <= 160 (got %d)", p.Lk);
 }
 
-static int attention_variant() {  // GD_ATTN=v1 selects the per-(clip, head) kernel above (A/B measurements)
-    static int v = 0;
-    if (!v) {
-        const char* e = getenv("GD_ATTN");
-        v = (e && e[0] == 'v' && e[1] == '1') ? 1 : 2;
-    }
-    return v;
+// GD_ATTN selects the kernel generation: v1 = one CTA per (clip, head), mma.sync; v2 (default) = persistent TMA-fed
+// mma.sync kernel; v3 = tcgen05/TMEM kernel for d_k = 64 (attention_tc.cu) - correct, but measured slower than v2 on
+// B200 in its current form (138-token joint attention, 256 clips: 86 us vs 74 us), so it stays opt-in.
+static int attention_variant() {
+    const char* e = getenv("GD_ATTN");
+    if (e && e[0] == 'v' && e[1] >= '1' && e[1] <= '3') return e[1] - '0';
+    return 2;
 }
 
 static int run_attention(const gd_attn_desc* d, bool fp32_in, void* stream) {
@@ -690,7 +670,11 @@ static int run_attention(const gd_attn_desc* d, bool fp32_in, void* stream) {
         return set_error(GD_ERR_INVALID, "gd_dconv_attention: need 0 < keys <= 160 (got %d), queries <= 1024", p.Lk);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     // bf16 rows whose segments fit a TMA box go to the persistent TMA-fed kernel
-    const bool tma_ok = !fp32_in && attention_variant() == 2 && p.q_rows[0] <= 256 && p.q_rows[1] <= 256 &&
+    const int variant = attention_variant();
+    if (!fp32_in && variant == 3 && d->d_k == 64 && p.q_rows[0] <= 256 && p.q_rows[1] <= 256 && p.kv_rows[0] <= 256 &&
+        p.kv_rows[1] <= 256 && p.Lq <= 256)
+        return launch_attention_tc(p, d->n_clips, s);
+    const bool tma_ok = !fp32_in && variant >= 2 && p.q_rows[0] <= 256 && p.q_rows[1] <= 256 &&
                         p.Lq <= 256 && (64 % d->d_k) == 0 && d->heads % (64 / d->d_k) == 0;
     if (tma_ok) {
         if (d->d_k == 32) return dispatch_kb_tma<32>(p, d->n_clips, s);

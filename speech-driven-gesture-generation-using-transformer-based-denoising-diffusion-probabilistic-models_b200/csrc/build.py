@@ -4,7 +4,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["api.cu", "gemm_tcgen05.cu", "gemm_resid_ln.cu", "elementwise.cu", "attention.cu"]
+SOURCES = ["api.cu", "gemm_tcgen05.cu", "gemm_resid_ln.cu", "elementwise.cu", "attention.cu", "attention_tc.cu"]
 OUT = os.path.join(os.path.dirname(HERE), "libgd_b200.so")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--compiler-options", "-fPIC",
          "-shared", "-lcudart"]
