@@ -184,6 +184,18 @@ def _ref_attention(q, k, v, taps, scale):
     (32, (40, 0), (32, 0), False, 333), (64, (7, 0), (7, 0), False, 3), (32, (160, 0), (160, 0), False, 40),
     (32, (300, 0), (100, 0), False, 3)])
 def test_dconv_attention(gd, dk, rows_q, rows_kv, f32, N):
+    _dconv_attention_case(gd, dk, rows_q, rows_kv, f32, N)
+
+
+@pytest.mark.parametrize("rows_q,rows_kv,N", [((34, 104), (34, 104), 90), ((104, 0), (104, 0), 7), ((34, 0), (34, 104), 5),
+                                               ((7, 0), (7, 0), 3), ((34, 0), (34, 0), 300), ((160, 0), (127, 0), 4)])
+def test_dconv_attention_tcgen05_variant(gd, rows_q, rows_kv, N, monkeypatch):
+    """The opt-in tcgen05/TMEM attention kernel (GD_ATTN=v3, d_k = 64): same reference, one and two 128-row query tiles."""
+    monkeypatch.setenv("GD_ATTN", "v3")
+    _dconv_attention_case(gd, 64, rows_q, rows_kv, False, N)
+
+
+def _dconv_attention_case(gd, dk, rows_q, rows_kv, f32, N):
     H = 8
     d_model = H * dk
     g = torch.Generator(device="cuda").manual_seed(dk + sum(rows_q))
