@@ -312,7 +312,7 @@ def run_b200(args):
     ach = gm["flops"] / (gm["ms"] * 1e-3) / 1e12
     step_ms = sum(a["ms"] for a in agg.values())
     total_flops = sum(a["flops"] for a in agg.values())
-    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel + gemm_resid_ln_kernel (tcgen05+TMA)", "achieved": ach, "peak": peak_tf,
+    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel" + (" + gemm_resid_ln_kernel" if "gemm_ln" in agg else "") + " (tcgen05+TMA)", "achieved": ach, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src,
                 "launches_per_step": gm["launches"], "share_of_step": gm["ms"] / step_ms,
                 "flops_per_step": gm["flops"], "avg_launch_us": 1e3 * gm["ms"] / gm["launches"]}
