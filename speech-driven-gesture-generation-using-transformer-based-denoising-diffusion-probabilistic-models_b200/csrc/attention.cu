@@ -672,7 +672,7 @@ static int run_attention(const gd_attn_desc* d, bool fp32_in, void* stream) {
     // bf16 rows whose segments fit a TMA box go to the persistent TMA-fed kernel
     const int variant = attention_variant();
     if (!fp32_in && variant == 3 && d->d_k == 64 && p.q_rows[0] <= 256 && p.q_rows[1] <= 256 && p.kv_rows[0] <= 256 &&
-        p.kv_rows[1] <= 256 && p.Lq <= 256)
+        p.kv_rows[1] <= 256 && p.Lq <= 144)
         return launch_attention_tc(p, d->n_clips, s);
     const bool tma_ok = !fp32_in && variant >= 2 && p.q_rows[0] <= 256 && p.q_rows[1] <= 256 &&
                         p.Lq <= 256 && (64 % d->d_k) == 0 && d->heads % (64 / d->d_k) == 0;

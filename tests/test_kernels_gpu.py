@@ -188,7 +188,8 @@ def test_dconv_attention(gd, dk, rows_q, rows_kv, f32, N):
 
 
 @pytest.mark.parametrize("rows_q,rows_kv,N", [((34, 104), (34, 104), 90), ((104, 0), (104, 0), 7), ((34, 0), (34, 104), 5),
-                                               ((7, 0), (7, 0), 3), ((34, 0), (34, 0), 300), ((160, 0), (127, 0), 4)])
+                                               ((7, 0), (7, 0), 3), ((34, 0), (34, 0), 300), ((144, 0), (160, 0), 4), ((129, 0), (17, 0), 3),
+                                               ((128, 0), (128, 0), 3)])
 def test_dconv_attention_tcgen05_variant(gd, rows_q, rows_kv, N, monkeypatch):
     """The opt-in tcgen05/TMEM attention kernel (GD_ATTN=v3, d_k = 64): same reference, one and two 128-row query tiles."""
     monkeypatch.setenv("GD_ATTN", "v3")
