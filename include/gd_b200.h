@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GD_ABI_VERSION 1
+#define GD_ABI_VERSION 2
 
 enum gd_status {
     GD_OK = 0,
@@ -112,6 +112,9 @@ typedef struct gd_ddpm_desc {
     const float* inpaint_mask;   /* (N, T) fp32, required with inpaint_seed                 */
     const float* inpaint_factor; /* [T] fp32 trans_factor ramp, required with inpaint_seed  */
     float clip_x0;            /* > 0: clamp x0 to [-clip, clip]; 0 = off (reference has none) */
+    const float* xa_add;      /* optional (N, C, T) fp32 added to x' before the bf16 cast into xa_bf16: the
+                                 loop-invariant `proj([inpaint_pose*mask | mask])` that Speech2GestureModelInpaint
+                                 adds to its input (models/model.py:155-166)                                        */
 } gd_ddpm_desc;
 
 /* Standalone update from an eps tensor laid out (N, C, T). */
@@ -203,8 +206,11 @@ int gd_scatter_step_row_f32(float* dst, const float* init, const float* table, c
 int gd_scatter_step_row_bf16(void* dst, const void* table, const int32_t* step_ptr, int32_t n_clips,
                              int32_t rows_per_clip, int32_t row_index, int32_t width, int32_t ld, void* stream);
 
-/* (N, C, T) fp32 -> bf16 token rows [N*T, ld] (cols >= C zeroed): builds the first emb_x operand from x_T. */
+/* (N, C, T) fp32 -> bf16 token rows [N*T, ld] (cols >= C zeroed): builds the first emb_x operand from x_T.
+ * `add` (optional, (N, C, T) fp32) is added before the cast (see gd_ddpm_desc.xa_add). */
 int gd_pack_pose_rows(const float* x, void* xa_bf16, int32_t n_clips, int32_t C, int32_t T, int32_t ld, void* stream);
+int gd_pack_pose_rows_add(const float* x, const float* add, void* xa_bf16, int32_t n_clips, int32_t C, int32_t T,
+                          int32_t ld, void* stream);
 
 /* fp32 -> bf16 row conversion (weights / conditioning repack): dst[r*ldd + c] = src[r*lds + c], c < cols;
  * columns [cols, cols_padded) are zero-filled. */

@@ -241,10 +241,22 @@ def speech_features(sd, wav):
 
 
 # ----------------------------------------------------------------------------- denoisers
-def denoiser(sd, model_type, heads, x_t, t, feats):
+def inpaint_offset(sd, inpaint_pose, inpaint_mask):
+    """Speech2GestureModelInpaint.myforward model.py:155-165: proj([pose*mask | mask]) with proj = Linear, SiLU, Linear,
+    SiLU, Linear.  inpaint_pose (N,T,C), inpaint_mask (N,T,1) -> (N,C,T) offset of the denoiser input."""
+    h = torch.cat([inpaint_pose * inpaint_mask, inpaint_mask], dim=-1)
+    h = F.silu(F.linear(h, sd["proj.0.weight"], sd["proj.0.bias"]))
+    h = F.silu(F.linear(h, sd["proj.2.weight"], sd["proj.2.bias"]))
+    return F.linear(h, sd["proj.4.weight"], sd["proj.4.bias"]).permute(0, 2, 1)
+
+
+def denoiser(sd, model_type, heads, x_t, t, feats, offset=None):
     """model(x_t (N,C,T), t (N,)) -> eps (N,C,T) given the (loop-invariant) speech features.
     tedexp: Speech2GestureModel.myforward model.py:41-73 + CrossAttention nn.py:428-447,90-125
-    beat:   Speech2GestureModelV2.myforward model.py:81-117 + OnewayCrossAttention nn.py:216-228,154-174"""
+    beat:   Speech2GestureModelV2.myforward model.py:81-117 + OnewayCrossAttention nn.py:216-228,154-174
+    inpaint: the tedexp wrapper applied to x_t + offset (inpaint_offset above)"""
+    if model_type == "inpaint":
+        x_t, model_type = x_t + offset, "default"
     d = sd["pose_decoder.emb_x.weight"].shape[0]
     z_low, z_mid, z_high = feats
     zt = step_token(sd, t, d).unsqueeze(1)  # (N,1,d)
@@ -336,7 +348,7 @@ def ddim_step(tabs, i, x, eps, blend=None):
 
 @torch.no_grad()
 def sample_chain(sd, model_type, heads, tabs, x_T, wav, tape, alg="ddpm", steps=None, blend=None,
-                 reencode_every_step=False, record=None):
+                 reencode_every_step=False, record=None, offset=None):
     """p_sample_loop / ddim_sample_loop — gaussian_diffusion.py:368-412,486-529.
     tape[k] is the k-th randn_like draw (loop order i = n-1 .. 0); `steps` restricts to the first
     `steps` iterations (bounded CPU baseline).  reencode_every_step=True reproduces the reference as
@@ -349,7 +361,7 @@ def sample_chain(sd, model_type, heads, tabs, x_T, wav, tape, alg="ddpm", steps=
             break
         t = torch.full((x.shape[0],), int(tabs["timestep_map"][i]), dtype=torch.long)
         f = speech_features(sd, wav) if reencode_every_step else feats
-        eps = denoiser(sd, model_type, heads, x, t, f)
+        eps = denoiser(sd, model_type, heads, x, t, f, offset=offset)
         if alg == "ddpm":
             x_next, x0 = ddpm_step(tabs, i, x, eps, tape[k] if tape is not None else torch.zeros_like(x), blend)
         else:

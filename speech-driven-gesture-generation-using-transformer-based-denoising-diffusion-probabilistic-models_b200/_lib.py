@@ -24,7 +24,8 @@ class DdpmDesc(C.Structure):
     _fields_ = [("x", c_vp), ("noise_tape", c_vp), ("coef_A", c_vp), ("coef_B", c_vp), ("coef_C1", c_vp),
                 ("coef_C2", c_vp), ("sigma", c_vp), ("step_ptr", c_vp), ("n_clips", c_i32), ("C", c_i32),
                 ("T", c_i32), ("eps_out", c_vp), ("x0_out", c_vp), ("xa_bf16", c_vp), ("ld_xa", c_i32),
-                ("inpaint_seed", c_vp), ("inpaint_mask", c_vp), ("inpaint_factor", c_vp), ("clip_x0", c_f32)]
+                ("inpaint_seed", c_vp), ("inpaint_mask", c_vp), ("inpaint_factor", c_vp), ("clip_x0", c_f32),
+                ("xa_add", c_vp)]
 
 
 class LnDesc(C.Structure):
@@ -56,6 +57,7 @@ SYMBOLS = {
     "gd_scatter_step_row_f32": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "gd_scatter_step_row_bf16": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "gd_pack_pose_rows": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "gd_pack_pose_rows_add": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "gd_cast_rows_bf16": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "gd_step_add": (c_i32, [c_vp, c_i32, c_vp]),
 }
@@ -80,7 +82,7 @@ def load():
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype, fn.argtypes = res, args
-    if lib.gd_abi_version() != 1:
+    if lib.gd_abi_version() != 2:
         raise GdError("libgd_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -68,9 +68,10 @@ __global__ void __launch_bounds__(256) ddpm_update_kernel(const gd_ddpm_desc u, 
         const int frame = (int)(i % u.T);
         const int c = (int)((i / u.T) % c_span);
         const int clip = (int)(i / ((size_t)u.T * c_span));
-        float xnext = 0.f;
+        float xnext = 0.f, xadd = 0.f;
         if (c < u.C) {
             const size_t idx = ((size_t)clip * u.C + c) * u.T + frame;
+            if (u.xa_add) xadd = __ldg(u.xa_add + idx);
             float m = 0.f, f = 0.f, seed = 0.f;
             if (inpaint) {
                 m = __ldg(u.inpaint_mask + (size_t)clip * u.T + frame);
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(256) ddpm_update_kernel(const gd_ddpm_desc u, 
         }
         if (u.xa_bf16)
             reinterpret_cast<__nv_bfloat16*>(u.xa_bf16)[((size_t)clip * u.T + frame) * u.ld_xa + c] =
-                __float2bfloat16_rn(xnext);
+                __float2bfloat16_rn(xnext + xadd);
     }
 }
 
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(256) scatter_row_bf16_kernel(__nv_bfloat16* __
 }
 
 // ------------------------------------------------------------------------------- layout helpers
-__global__ void __launch_bounds__(256) pack_pose_rows_kernel(const float* __restrict__ x,
+__global__ void __launch_bounds__(256) pack_pose_rows_kernel(const float* __restrict__ x, const float* __restrict__ add,
                                                              __nv_bfloat16* __restrict__ xa, int n_clips, int C,
                                                              int T, int ld) {
     pdl_launch_dependents();
@@ -149,7 +150,12 @@ __global__ void __launch_bounds__(256) pack_pose_rows_kernel(const float* __rest
         const size_t row = i / ld;
         const int frame = (int)(row % T);
         const size_t clip = row / T;
-        xa[i] = __float2bfloat16_rn(c < C ? x[(clip * C + c) * T + frame] : 0.f);
+        float v = 0.f;
+        if (c < C) {
+            const size_t idx = (clip * C + c) * T + frame;
+            v = add ? x[idx] + __ldg(add + idx) : x[idx];
+        }
+        xa[i] = __float2bfloat16_rn(v);
     }
 }
 
@@ -251,16 +257,21 @@ extern "C" int gd_scatter_step_row_bf16(void* dst, const void* table, const int3
     return GD_OK;
 }
 
-extern "C" int gd_pack_pose_rows(const float* x, void* xa_bf16, int32_t n_clips, int32_t C, int32_t T, int32_t ld,
-                                 void* stream) {
+extern "C" int gd_pack_pose_rows_add(const float* x, const float* add, void* xa_bf16, int32_t n_clips, int32_t C, int32_t T,
+                                     int32_t ld, void* stream) {
     if (!x || !xa_bf16 || n_clips <= 0 || C <= 0 || T <= 0 || ld < C)
         return set_error(GD_ERR_INVALID, "gd_pack_pose_rows: bad argument");
     const size_t total = (size_t)n_clips * T * ld;
     GD_CUDA_CHECK(launch_k(pack_pose_rows_kernel, grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), 1, x,
-                           reinterpret_cast<__nv_bfloat16*>(xa_bf16), n_clips, C, T, ld));
+                           add, reinterpret_cast<__nv_bfloat16*>(xa_bf16), n_clips, C, T, ld));
     count_launch();
     GD_CUDA_CHECK(cudaGetLastError());
     return GD_OK;
+}
+
+extern "C" int gd_pack_pose_rows(const float* x, void* xa_bf16, int32_t n_clips, int32_t C, int32_t T, int32_t ld,
+                                 void* stream) {
+    return gd_pack_pose_rows_add(x, nullptr, xa_bf16, n_clips, C, T, ld, stream);
 }
 
 extern "C" int gd_cast_rows_bf16(const float* src, int32_t lds, void* dst, int32_t ldd, int32_t rows, int32_t cols,

@@ -151,6 +151,7 @@ __device__ __forceinline__ void epilogue_ddpm_chunk(const GemmParams& p, const D
     const int ncol = u.C - col0;  // columns >= ncol of this chunk are padding (warp-uniform)
     float* const xp = u.x + off0;
     const float* const zp = tape_t ? tape_t + off0 : nullptr;
+    const float* const xa_add = u.xa_add ? u.xa_add + off0 : nullptr;  // Inpaint model: loop-invariant input offset
     float* const eps_o = (AUX && u.eps_out) ? u.eps_out + off0 : nullptr;
     float* const x0_o = (AUX && u.x0_out) ? u.x0_out + off0 : nullptr;
     float m = 0.f, f = 0.f;
@@ -186,7 +187,7 @@ __device__ __forceinline__ void epilogue_ddpm_chunk(const GemmParams& p, const D
                     if (eps_o) eps_o[j * T] = eps;
                     if (x0_o) x0_o[j * T] = x0;
                 }
-                xn[i] = xnext;
+                xn[i] = xa_add ? xnext + __ldg(xa_add + j * T) : xnext;
             }
         }
         if (u.xa_bf16) {

@@ -155,8 +155,9 @@ class GaussianSpacedDiffusion(GaussianDiffusion):
             raise ValueError("model_kwargs['wav'] is required")
         if noise is None:
             noise = th.randn(*shape, device=device)
+        offset = model.input_offset(model_kwargs) if hasattr(model, "input_offset") else None
         chain.begin(noise.to(device), wav.to(device), denoise_fn=denoise_fn, noise_tape=noise_tape,
-                    need_tape=(alg == "ddpm"))
+                    need_tape=(alg == "ddpm"), input_offset=offset)
         if progressive:
             return chain.iterate(progress)
         return chain.run(progress)
@@ -201,7 +202,8 @@ class GaussianSpacedDiffusion(GaussianDiffusion):
         if wav is None:
             raise ValueError("model_kwargs['wav'] is required")
         chain = chain_for(model, self, shape, "ddpm", device)
-        chain.begin(th.zeros(shape, device=device), wav.to(device), need_tape=False)
+        offset = model.input_offset(model_kwargs) if hasattr(model, "input_offset") else None
+        chain.begin(th.zeros(shape, device=device), wav.to(device), need_tape=False, input_offset=offset)
         n = self.num_timesteps
         tab = lambda a: th.from_numpy(a).to(device).float()  # noqa: E731  (float64 table -> fp32 at gather, :691)
         sa, s1a = tab(self.sqrt_alphas_cumprod), tab(self.sqrt_one_minus_alphas_cumprod)

@@ -202,6 +202,7 @@ class SamplingChain:
         self.x0 = th.zeros_like(self.x)
         self.tape = None
         self.blend = None
+        self.xa_add = None  # Inpaint model: (N,C,T) offset added when the bf16 emb_x operand is built
         self.plan = None
         self.side = th.cuda.Stream(device=device)
         import os
@@ -301,6 +302,7 @@ class SamplingChain:
         if self.blend is not None:
             u.inpaint_seed, u.inpaint_mask, u.inpaint_factor = _p(self.blend.seed), _p(self.blend.mask), _p(self.blend.factor)
         u.clip_x0 = 0.0
+        u.xa_add = _p(self.xa_add)
         return u
 
     def _attn_block(self, ops, a, rows_lo, rows_hi, segs, xn, qkv, ao, H, n_heads, next_ln=None):
@@ -447,8 +449,9 @@ class SamplingChain:
         return ops
 
     # ------------------------------------------------------------------ public driver
-    def begin(self, x_T, wav, denoise_fn=None, noise_tape=None, need_tape=True):
-        """Load x_T, compute the conditioning once, (re)build the plan, reset the step counter."""
+    def begin(self, x_T, wav, denoise_fn=None, noise_tape=None, need_tape=True, input_offset=None):
+        """Load x_T, compute the conditioning once, (re)build the plan, reset the step counter.  `input_offset`
+        (N,C,T) is the Inpaint model's loop-invariant offset of the denoiser input (model.py:161-165)."""
         from .diffusion import InpaintBlend
         if denoise_fn is not None and not isinstance(denoise_fn, InpaintBlend):
             raise NotImplementedError("denoise_fn must be an InpaintBlend (the fused in-paint epilogue); "
@@ -475,7 +478,15 @@ class SamplingChain:
                     self.tape = tp
         blend_key = None if denoise_fn is None else "blend"
         cond = self._conditioning(wav)
-        key = (cond["Tm"], blend_key, need_tape, _p(self.tape) if need_tape else 0)
+        if input_offset is not None:
+            if tuple(input_offset.shape) != (self.N, self.C, self.T):
+                raise ValueError(f"input_offset shape {tuple(input_offset.shape)} != {(self.N, self.C, self.T)}")
+            if self.xa_add is None:
+                self.xa_add = th.empty(self.N, self.C, self.T, device=dev)
+            self.xa_add.copy_(input_offset.float())
+        elif self.xa_add is not None:
+            self.xa_add = None
+        key = (cond["Tm"], blend_key, need_tape, _p(self.tape) if need_tape else 0, _p(self.xa_add))
         if self.plan is None or key != self._plan_key:
             self.blend = denoise_fn
             self.Tm = cond["Tm"]
@@ -494,8 +505,7 @@ class SamplingChain:
                 self.blend.mask.copy_(denoise_fn.mask)
                 self.blend.factor.copy_(denoise_fn.factor)
         self.x.copy_(x_T.float())
-        gd.check(self.L.lib.gd_pack_pose_rows(_p(self.x), _p(self.xa), self.N, self.C, self.T, _POSE_PAD, self.L.stream()),
-                 "gd_pack_pose_rows")
+        self._pack_pose_rows()
         self.step.fill_(self.n_steps - 1)
 
     def step_eager(self):
@@ -521,9 +531,12 @@ class SamplingChain:
     def set_state(self, x, i):
         """Teacher forcing: overwrite the sample and the loop index (parity harness)."""
         self.x.copy_(x.to(self.device).float())
-        gd.check(self.L.lib.gd_pack_pose_rows(_p(self.x), _p(self.xa), self.N, self.C, self.T, _POSE_PAD, self.L.stream()),
-                 "gd_pack_pose_rows")
+        self._pack_pose_rows()
         self.step.fill_(int(i))
+
+    def _pack_pose_rows(self):
+        gd.check(self.L.lib.gd_pack_pose_rows_add(_p(self.x), _p(self.xa_add), _p(self.xa), self.N, self.C, self.T, _POSE_PAD,
+                                                  self.L.stream()), "gd_pack_pose_rows_add")
 
     def _ensure_graph(self):
         if self.graph is not None or not self.use_graph:

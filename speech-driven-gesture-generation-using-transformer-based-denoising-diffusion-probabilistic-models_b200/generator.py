@@ -50,7 +50,14 @@ class Generator:
         if noise is None:
             noise = th.randn(shape, device=device)
         kw = {"noise_tape": noise_tape} if sample_alg == "ddpm" else {}
-        sample = sample_func(self.model, shape, noise=noise, denoise_fn=denoise_fn, model_kwargs={"wav": wavs},
+        model_kwargs = {"wav": wavs}
+        if getattr(self.model, "model_type", None) == "inpaint":  # generator.py:244-250
+            assert len(inpaint_poses.shape) == 3
+            assert len(inpaint_masks.shape) == 3
+            assert inpaint_masks.size()[:2] == inpaint_poses.size()[:2]
+            model_kwargs["inpaint_pose"] = inpaint_poses.to(device).transpose(0, 1)  # -> (T,N,C)
+            model_kwargs["inpaint_mask"] = inpaint_masks.to(device).transpose(0, 1)  # -> (T,N,1)
+        sample = sample_func(self.model, shape, noise=noise, denoise_fn=denoise_fn, model_kwargs=model_kwargs,
                              device=device, progress=progress, **kw)["sample"].transpose(1, 2)  # -> (N,T,C)
         return self.tensor2dtype(sample.contiguous(), return_dtype)  # a copy: the chain's buffers are reused
 
@@ -135,11 +142,18 @@ class Generator:
 
     @th.no_grad()
     def eval_bpd(self, poses: th.Tensor, wavs: th.Tensor, pose_seed_len: int = None, noise_tape: th.Tensor = None):
-        """generator.py:197-216: variational bound of `poses` (N,T,C) given `wavs`, on the device the model lives on.
-        (The `inpaint` model variant that needs pose_seed_len is not one of the shipped configs and is not built.)"""
+        """generator.py:197-216: variational bound of `poses` (N,T,C) given `wavs`, on the device the model lives on."""
         device = next(self.model.parameters()).device
-        return self.diffusion.calc_bpd_loop(self.model, x_start=poses.to(device).transpose(1, 2),  # -> (N,C,T)
-                                            model_kwargs={"wav": wavs.to(device)}, noise_tape=noise_tape)
+        poses = poses.to(device)
+        model_kwargs = {"wav": wavs.to(device)}
+        if getattr(self.model, "model_type", None) == "inpaint":
+            assert pose_seed_len is not None, "Provide pose_seed_len for inpaint model."
+            inpaint_masks = th.ones_like(poses)[:, :, :1]  # (N,T,1)
+            inpaint_masks[:, pose_seed_len:] = 0
+            model_kwargs["inpaint_pose"] = poses.clone().transpose(0, 1)  # (T,N,C)
+            model_kwargs["inpaint_mask"] = inpaint_masks.transpose(0, 1)  # (T,N,1)
+        return self.diffusion.calc_bpd_loop(self.model, x_start=poses.transpose(1, 2),  # -> (N,C,T)
+                                            model_kwargs=model_kwargs, noise_tape=noise_tape)
 
     @staticmethod
     def tensor2dtype(x: th.Tensor, dtype: str):

@@ -12,13 +12,16 @@ class Speech2GestureDenoiser(nn.Module):
     """model(x_t (N,C,T) fp32, t (N,) int64, wav=(N,T_wav)) -> eps (N,C,T) fp32   (models/model.py:12-15).
 
     model_type 'default' = tedexp-ours wrapper (memory = [z_t ; low ; mid ; high], model.py:41-73);
-    's2g_v2' = beat-ours wrapper (adds `blend_layer`, memory = [z_t ; blend(low|mid|high)], model.py:76-117).
+    's2g_v2' = beat-ours wrapper (adds `blend_layer`, memory = [z_t ; blend(low|mid|high)], model.py:76-117);
+    'inpaint' = the default wrapper whose input is offset by `proj([inpaint_pose*mask | mask])`, a zero-initialised
+    3-layer SiLU MLP (model.py:120-166); it takes the extra kwargs inpaint_pose (T,N,C) and inpaint_mask (T,N,1).
     Attributes `precision` ('bf16' | 'fp32act'), `graph_steps`, `use_graph` steer the engine.
     """
 
-    def __init__(self, model_type, d_pose, d_model, speech_encoder, pose_decoder, diffusion_step_encoder):
+    def __init__(self, model_type, d_pose, d_model, speech_encoder, pose_decoder, diffusion_step_encoder, dropout_prob=0.0,
+                 pose_seed_len=None):
         super().__init__()
-        if model_type not in ("default", "s2g_v2"):
+        if model_type not in ("default", "s2g_v2", "inpaint"):
             raise ValueError(f"Unsupported model_type {model_type}")
         self.model_type = model_type
         self.diffusion_step_encoder = diffusion_step_encoder
@@ -27,6 +30,14 @@ class Speech2GestureDenoiser(nn.Module):
         self.d_pose, self.d_model = d_pose, d_model
         if model_type == "s2g_v2":
             self.blend_layer = nn.Linear(3 * d_model, d_model)
+        if model_type == "inpaint":
+            self.pose_seed_len = pose_seed_len
+            self.proj = nn.Sequential(nn.Linear(d_pose + 1, d_model), nn.SiLU(), nn.Linear(d_model, d_model), nn.SiLU(),
+                                      nn.Linear(d_model, d_pose), nn.Dropout(dropout_prob))
+            for m in self.proj:  # zero init as GLIDE (model.py:147-153)
+                if isinstance(m, nn.Linear):
+                    m.weight.data.zero_()
+                    m.bias.data.zero_()
         self.precision, self.graph_steps, self.use_graph = "bf16", 1, True
         self.weights_version = 0
         self._packed = None
@@ -61,6 +72,26 @@ class Speech2GestureDenoiser(nn.Module):
         print("[Info] Number of parameters: {:,}".format(n))
         return n
 
+    def input_offset(self, model_kwargs):
+        """Inpaint model: proj([inpaint_pose*mask | mask]) as an (N,C,T) fp32 tensor (model.py:161-165).  It does not
+        depend on the timestep, so it is evaluated once per chain (three small fp32 Linears) and the kernels add it to
+        the sample when they build the bf16 operand of emb_x.  None for the other model types."""
+        if self.model_type != "inpaint":
+            return None
+        pose, mask = model_kwargs.get("inpaint_pose"), model_kwargs.get("inpaint_mask")
+        if pose is None or mask is None:
+            raise ValueError("the inpaint model needs model_kwargs['inpaint_pose'] (T,N,C) and ['inpaint_mask'] (T,N,1)")
+        dev = next(self.parameters()).device
+        pose, mask = pose.to(dev).float(), mask.to(dev).float()
+        prev = th.backends.cuda.matmul.allow_tf32
+        th.backends.cuda.matmul.allow_tf32 = False  # reference math is fp32
+        try:
+            with th.no_grad():
+                delta = self.proj(th.cat([pose * mask, mask], dim=-1))  # (T,N,C)
+        finally:
+            th.backends.cuda.matmul.allow_tf32 = prev
+        return delta.permute(1, 2, 0).contiguous()  # -> (N,C,T)
+
     # -- forward: one denoiser evaluation -------------------------------------------------------------
     @th.no_grad()
     def forward(self, x_t, t, **model_kwargs):
@@ -78,7 +109,7 @@ class Speech2GestureDenoiser(nn.Module):
             raise NotImplementedError("per-clip timesteps are not supported: the sampling loops use one t per step")
         i = self._diffusion.timestep_map.index(t0)
         chain = chain_for(self, self._diffusion, tuple(x_t.shape), "ddpm", x_t.device, use_graph=False)
-        chain.begin(x_t, model_kwargs["wav"].to(x_t.device), need_tape=False)
+        chain.begin(x_t, model_kwargs["wav"].to(x_t.device), need_tape=False, input_offset=self.input_offset(model_kwargs))
         chain.set_state(x_t, i)
         chain.step_eager()
         return chain.eps.clone()

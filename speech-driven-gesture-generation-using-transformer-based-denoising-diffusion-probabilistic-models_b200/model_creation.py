@@ -69,11 +69,15 @@ def create_model(d_pose, model_params, lr=1e-2, weight_decay=None, scheduler_par
     step_encoder = StepEncoderParams(model_params.d_model, model_params.dropout_prob)
     diffusion = create_diffusion(model_params.get("Diffusion"), is_training)
 
-    if model_params.type == "inpaint":
-        raise NotImplementedError("model type 'inpaint' is not selected by either shipped config")
-    if model_params.type not in ("default", "s2g_v2"):
+    if model_params.type not in ("default", "s2g_v2", "inpaint"):
         raise ValueError(f"Unsupported model_type {model_params.type}")
-    model = Speech2GestureDenoiser(model_params.type, d_pose, model_params.d_model, speech_encoder, decoder, step_encoder)
+    if model_params.type == "inpaint" and decoder_params.type != "cross_attention":
+        raise NotImplementedError("the inpaint wrapper is built on the default (tedexp) memory layout: cross_attention decoder only")
+    extra = {}
+    if model_params.type == "inpaint":  # model_creation.py:134-143
+        extra = {"dropout_prob": model_params.dropout_prob, "pose_seed_len": model_params.Generate.pose_seed_len}
+    model = Speech2GestureDenoiser(model_params.type, d_pose, model_params.d_model, speech_encoder, decoder, step_encoder,
+                                   **extra)
     model.bind_diffusion(diffusion)
 
     optimizer = th.optim.AdamW(model.parameters(), lr=lr, weight_decay=weight_decay)

@@ -179,6 +179,47 @@ def sequence():
     print("sequence written", {k: v.shape for k, v in out.items()})
 
 
+def inpaint():
+    """Model type 'inpaint' (Speech2GestureModelInpaint, model.py:120-166; not one of the shipped configs): the tedexp
+    decoder with the seed-pose MLP, ddim20 process.  The reference zero-initialises `proj`, which would make the variant
+    indistinguishable from 'default'; the boosted weights make it non-trivial.  Saved: proj(...) offset, teacher-forced eps at
+    two steps, the in-painted 20-step ancestral chain through Generator.generate_sample."""
+    mp, d_pose, T, L = ref_params("tedexp", "ddim20")
+    mp["type"] = "inpaint"
+    mp["Generate"] = JsonConfig({"pose_seed_len": 4})
+    th.manual_seed(0)
+    model, diffusion, *_ = create_model(d_pose=d_pose, model_params=mp, is_training=False)
+    model.eval()
+    model.load_state_dict(boosted_state_dict(model.state_dict(), seed=1))
+    n = 2
+    wav = synthetic_wav(n, L, seed=61)
+    g = th.Generator().manual_seed(62)
+    seed_poses = th.randn(n, T, d_pose, generator=g)
+    masks = th.ones(n, T, 1)
+    masks[:, 4:] = 0
+    x_T, tape = noise_tape((n, d_pose, T), diffusion.num_timesteps, seed=63)
+    out = {}
+    kw = {"wav": wav, "inpaint_pose": seed_poses.transpose(0, 1), "inpaint_mask": masks.transpose(0, 1)}
+    with th.no_grad():
+        out["offset"] = model.proj(th.cat([kw["inpaint_pose"] * kw["inpaint_mask"], kw["inpaint_mask"]], -1)).permute(1, 2, 0).numpy()
+        for i in (19, 3):
+            x = th.randn(n, d_pose, T, generator=th.Generator().manual_seed(100 + i))
+            t = th.full((n,), diffusion.timestep_map[i], dtype=th.long)
+            out[f"eps.{i}"] = model(x, t, **kw).numpy()
+    it = iter(tape)
+    real = th.randn_like
+    th.randn_like = lambda x: next(it)
+    try:
+        res = Generator(model, diffusion).generate_sample((n, d_pose, T), wav, noise=x_T, inpaint_poses=seed_poses,
+                                                          inpaint_masks=masks, sample_alg="ddpm", trans_factor=0.5,
+                                                          pose_seed_len=4, device="cpu", progress=False)
+    finally:
+        th.randn_like = real
+    out["ddpm20_inpaint.final"] = res.numpy()
+    np.savez_compressed(os.path.join(HERE, "tedexp_inpaint_model_golden.npz"), **out)
+    print("inpaint model written", {k: v.shape for k, v in out.items()}, float(np.abs(out["offset"]).mean()))
+
+
 def bpd():
     """Variational bound through the reference's Generator.eval_bpd (generator.py:197-216 -> calc_bpd_loop): beat-ours,
     20-step respaced process, boosted weights, fixed poses / speech / per-step noise."""
@@ -218,3 +259,5 @@ if __name__ == "__main__":
         sequence()
     if what in ("bpd", "all"):
         bpd()
+    if what in ("inpaint", "all"):
+        inpaint()

@@ -178,3 +178,34 @@ def test_oracle_bpd_terms():
     out = orc.bpd_loop(model.state_dict(), params.type, params.Decoder.heads, tabs, poses.transpose(1, 2), wav, tape)
     for k in ("total_bpd", "prior_bpd", "x_start_mse", "vb", "mse"):
         assert rel_l2(out[k], g[k]) < 1e-3, k
+
+
+def test_oracle_inpaint_model_variant():
+    """Model type 'inpaint' (seed-pose MLP offset on the denoiser input): oracle vs the reference's own model and its
+    Generator.generate_sample (tedexp decoder, ddim20 process, boosted weights incl. a non-zero `proj`)."""
+    import numpy as np
+    from util import GOLDEN
+    g = np.load(f"{GOLDEN}/tedexp_inpaint_model_golden.npz")
+    model, diffusion, C, T, L, params = build("tedexp", "boost", respacing="ddim20", model_type="inpaint")
+    sd = model.state_dict()
+    assert {"proj.0.weight", "proj.2.bias", "proj.4.weight"} <= set(sd) and model.pose_seed_len == 4
+    tabs = orc.spaced_diffusion_tables("linear", 1000, "ddim20")
+    wav = synthetic_wav(2, L, seed=61)
+    seed_poses = th.randn(2, T, C, generator=th.Generator().manual_seed(62))
+    masks = th.ones(2, T, 1)
+    masks[:, 4:] = 0
+    off = orc.inpaint_offset(sd, seed_poses, masks)
+    assert rel_l2(off, g["offset"]) < 1e-5
+    feats = orc.speech_features(sd, wav)
+    heads = params.Decoder.heads
+    for i in (19, 3):
+        x = th.randn(2, C, T, generator=th.Generator().manual_seed(100 + i))
+        t = th.full((2,), int(tabs["timestep_map"][i]), dtype=th.long)
+        with th.no_grad():
+            eps = orc.denoiser(sd, "inpaint", heads, x, t, feats, offset=off)
+        assert rel_l2(eps, g[f"eps.{i}"]) < 1e-3
+    x_T, tape = noise_tape((2, C, T), 20, seed=63)
+    f = orc.transition_factor(0.5, 4, T)
+    out = orc.sample_chain(sd, "inpaint", heads, tabs, x_T, wav, tape, alg="ddpm", offset=off,
+                           blend=lambda x0: orc.inpaint_blend(x0, seed_poses, masks, f))
+    assert rel_l2(out.transpose(1, 2), g["ddpm20_inpaint.final"]) < 1e-3

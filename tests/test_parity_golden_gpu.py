@@ -130,3 +130,32 @@ def test_eval_bpd_vs_reference():
         err = rel_l2(out[k], g[k])
         print(f"[beat] eval_bpd {k}: rel-L2 {err:.3e}")
         assert err < 2e-2, (k, err)
+
+
+def test_inpaint_model_variant_vs_reference():
+    """Model type 'inpaint' on the CUDA path: teacher-forced eps (the offset enters through gd_pack_pose_rows_add / the DDPM
+    epilogue's xa_add) and the in-painted 20-step ancestral chain through Generator.generate_sample, vs the reference."""
+    import numpy as np
+    from gesture_b200.generator import Generator
+    from util import GOLDEN
+    g = np.load(f"{GOLDEN}/tedexp_inpaint_model_golden.npz")
+    model, diffusion, C, T, L, params = build("tedexp", "boost", respacing="ddim20", device="cuda", model_type="inpaint")
+    wav = synthetic_wav(2, L, seed=61)
+    seed_poses = th.randn(2, T, C, generator=th.Generator().manual_seed(62))
+    masks = th.ones(2, T, 1)
+    masks[:, 4:] = 0
+    kw = {"wav": wav.cuda(), "inpaint_pose": seed_poses.transpose(0, 1).cuda(), "inpaint_mask": masks.transpose(0, 1).cuda()}
+    assert rel_l2(model.input_offset(kw), g["offset"]) < 1e-5
+    for i in (19, 3):
+        x = th.randn(2, C, T, generator=th.Generator().manual_seed(100 + i)).cuda()
+        t = th.full((2,), diffusion.timestep_map[i], dtype=th.long, device="cuda")
+        err = rel_l2(model(x, t, **kw), g[f"eps.{i}"])
+        print(f"[tedexp/inpaint-model] eps step {i}: rel-L2 {err:.3e}")
+        assert err < 2e-2, err
+    x_T, tape = noise_tape((2, C, T), 20, seed=63)
+    out = Generator(model, diffusion).generate_sample((2, C, T), wav, noise=x_T, inpaint_poses=seed_poses, inpaint_masks=masks,
+                                                      sample_alg="ddpm", trans_factor=0.5, pose_seed_len=4, device="cuda",
+                                                      progress=False, noise_tape=tape)
+    err = rel_l2(out, g["ddpm20_inpaint.final"])
+    print(f"[tedexp/inpaint-model] ddpm20 in-painted chain: rel-L2 {err:.3e}")
+    assert err < 2e-2, err

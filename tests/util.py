@@ -18,10 +18,13 @@ from gesture_b200.synthetic import boosted_state_dict, noise_tape, state_dict_di
 SHORT = {"beat": "beat-ours", "tedexp": "tedexp-ours"}
 
 
-def build(name, weights="boost", respacing="", device="cpu"):
-    """-> (model, diffusion, d_pose, T, wav_len, flat params).  weights: 'init' (seed-0 default init) | 'boost'."""
+def build(name, weights="boost", respacing="", device="cpu", model_type=None):
+    """-> (model, diffusion, d_pose, T, wav_len, flat params).  weights: 'init' (seed-0 default init) | 'boost'.
+    model_type='inpaint' switches the wrapper (Speech2GestureModelInpaint, tedexp decoder only)."""
     params, d_pose, T, L = preset(SHORT[name])
     params["Diffusion"]["timestep_respacing"] = respacing
+    if model_type is not None:
+        params["type"] = model_type
     th.manual_seed(0)
     model, diffusion, *_ = create_model(d_pose, params)
     model.eval()
