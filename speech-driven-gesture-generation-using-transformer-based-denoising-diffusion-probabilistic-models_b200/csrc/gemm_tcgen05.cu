@@ -370,6 +370,72 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int row0 = m0 + quad * 32;
             const int row = row0 + lane;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * WCOLS;
+            // the accumulator stage goes back to the MMA issuer as soon as this warp's last TMEM load has landed in
+            // registers - not after the stores - so tile i+2 can start while tile i is still being written out
+            auto release_accumulator = [&]() {
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CL == 1)
+                        mbar_arrive(&acc_empty_bar[acc]);
+                    else  // the MMA issuer lives in the leader CTA
+                        mbar_arrive_cluster(map_to_cta(smem_u32(&acc_empty_bar[acc]), 0));
+                }
+            };
+            if constexpr (MODE == MODE_TMA_BF16 && WCOLS >= 64) {
+                // bf16 output, 64 columns (one 128-B swizzled row per lane) per TMA store: half as many fences / stores /
+                // staging hand-offs as 32-column chunks, and the next TMEM load is in flight while this one is stored
+                constexpr int NSC = WCOLS / 64;
+                uint32_t v[64];
+                tmem_ld_32x32b_x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                tmem_ld_32x32b_x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+#pragma unroll 1
+                for (int sc = 0; sc < NSC; ++sc) {
+                    const int col0 = n0 + half * WCOLS + sc * 64;
+                    tmem_ld_wait();
+                    uint32_t w[32];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        float4 b[8];
+                        if (has_bias) {
+                            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0 + h * 32);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) b[j] = __ldg(b4 + j);
+                        }
+                        float r[32];
+                        add_bias_chunk(r, *reinterpret_cast<const uint32_t(*)[32]>(&v[32 * h]), b, has_bias);
+                        if (p.act == GD_ACT_RELU2) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float m = fmaxf(r[j], 0.f);
+                                r[j] = m * m;
+                            }
+                        } else if (p.act == GD_ACT_SILU) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) r[j] = apply_act(r[j], GD_ACT_SILU);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) w[16 * h + j] = pack_bf16x2(r[2 * j], r[2 * j + 1]);
+                    }
+                    if (sc + 1 < NSC) {
+                        tmem_ld_32x32b_x32(taddr + (sc + 1) * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                        tmem_ld_32x32b_x32(taddr + (sc + 1) * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+                    } else {
+                        release_accumulator();
+                    }
+                    if (lane == 0) bulk_wait_group_read0();  // the previous store has finished READING the staging tile
+                    __syncwarp();
+                    uint4* st4 = reinterpret_cast<uint4*>(stg_base);  // 128-B rows, SWIZZLE_128B: chunk ^= row & 7
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) st4[lane * 8 + (j ^ (lane & 7))] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+                    fence_proxy_async();  // make the generic-proxy smem writes visible to the TMA engine
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmap_out, stg_base, col0, row0);
+                        bulk_commit_group();
+                    }
+                }
+            } else {
 #pragma unroll 1
             for (int c = 0; c < WCOLS / 32; ++c) {
                 const int col0 = n0 + half * WCOLS + c * 32;
@@ -384,6 +450,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         for (int j = 0; j < 8; ++j) b[j] = __ldg(b4 + j);
                     }
                     tmem_ld_wait();
+                    if (c == WCOLS / 32 - 1) release_accumulator();
                     float r[32];
                     add_bias_chunk(r, v, b, has_bias);
                     if (p.act == GD_ACT_RELU2) {
@@ -440,15 +507,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         } else
                             epilogue_direct_chunk(p, row, col0, v);
                     }
+                    if (c == WCOLS / 32 - 1) release_accumulator();
                 }
             }
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) {
-                if (CL == 1)
-                    mbar_arrive(&acc_empty_bar[acc]);
-                else  // the MMA issuer lives in the leader CTA
-                    mbar_arrive_cluster(map_to_cta(smem_u32(&acc_empty_bar[acc]), 0));
             }
         }
         if ((MODE == MODE_TMA_BF16 || MODE == MODE_TMA_F32) && lane == 0) bulk_wait_group0();
@@ -495,9 +556,9 @@ static int launch_gemm_cl(const GemmParams& p, const void* A, int lda, const voi
     rc = make_tmap_2d_bf16(&tb, W, p.N, p.K, ldw, BN / CL);
     if (rc) return rc;
     tout = ta;  // unused unless a TMA epilogue is selected
-    if (MODE == MODE_TMA_BF16)
-        rc = make_tmap_2d(&tout, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.out_bf16, p.M, p.N, p.ldo_bf16, 32, 32,
-                          CU_TENSOR_MAP_SWIZZLE_64B);
+    if (MODE == MODE_TMA_BF16)  // 64-column (128-B) boxes whenever an epilogue warp owns at least 64 columns of the tile
+        rc = make_tmap_2d(&tout, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.out_bf16, p.M, p.N, p.ldo_bf16, BN / 2 >= 64 ? 64 : 32, 32,
+                          BN / 2 >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
     else if (MODE == MODE_TMA_F32)
         rc = make_tmap_2d(&tout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.out_f32, p.M, p.N, p.ldo_f32, 32, 32,
                           CU_TENSOR_MAP_SWIZZLE_128B);
