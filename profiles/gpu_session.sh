@@ -1,14 +1,9 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_kernels_gpu.py -x -q -k "linear" 2>&1 | tail -3
-timeout 300 python profiles/kernel_bench.py gemm --out gpurun_out/kb_gemm_e64.jsonl 2>&1 | python -c "
-import sys,json
-for l in sys.stdin:
-    if l.startswith('{'):
-        d=json.loads(l); print(d['M'], d['N'], d['K'], d['mode'], d['us'], d['TFLOPs'])"
-timeout 300 python profiles/cublas_ref.py 2>/dev/null | python -c "
-import sys,json
-for l in sys.stdin:
-    if l.startswith('{'):
-        d=json.loads(l); print('cublas', d['M'], d['N'], d['K'], d['us'], d['TFLOPs'])"
-for w in tedexp-ours beat-ours; do timeout 300 python bench.py --workload $w --steps 1 --warmup 1 --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('$w', round(d['value'],1), round(d['ms_per_denoise_step'],3), {k:v['ms_per_step'] for k,v in d['kernel_breakdown'].items()}, d['clocks']['sm_mhz'])"; done
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 900 python bench.py > gpurun_out/bench_v11_tedexp256.json 2> gpurun_out/bench_v11.err; tail -c 200 gpurun_out/bench_v11.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_v11_tedexp256.json')); print(d['value'], d['ms_per_denoise_step'], d['e2e']['value'], d['roofline']['achieved'], d['roofline']['traffic'], d['clocks'], {k:v['ms_per_step'] for k,v in d['kernel_breakdown'].items()})"
+timeout 600 python bench.py --workload beat-ours > gpurun_out/bench_v11_beat1024.json 2>/dev/null; python -c "
+import json; d=json.load(open('gpurun_out/bench_v11_beat1024.json')); print(d['value'], d['ms_per_denoise_step'], d['e2e']['value'], d['roofline']['achieved'], d['clocks'], {k:v['ms_per_step'] for k,v in d['kernel_breakdown'].items()})"
+timeout 600 python bench.py --workload beat-ours-4x --no-cpu-baseline > gpurun_out/bench_v11_beat4x64.json 2>/dev/null; python -c "
+import json; d=json.load(open('gpurun_out/bench_v11_beat4x64.json')); print(d['value'], d['ms_per_denoise_step'])"
