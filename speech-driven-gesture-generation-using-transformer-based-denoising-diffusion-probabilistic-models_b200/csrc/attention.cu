@@ -634,8 +634,8 @@ static int dispatch_kb_tma(const AttnParams& p, int n_clips, cudaStream_t s) {
 }
 
 // GD_ATTN selects the kernel generation: v1 = one CTA per (clip, head), mma.sync; v2 (default) = persistent TMA-fed
-// mma.sync kernel; v3 = tcgen05/TMEM kernel for d_k = 64 (attention_tc.cu) - correct, but measured slower than v2 on
-// B200 in its current form (138-token joint attention, 256 clips: 86 us vs 74 us), so it stays opt-in.
+// mma.sync kernel; v3 = warp-specialised tcgen05/TMEM pipeline for d_k = 64 (attention_tc.cu) - correct, but on B200 it
+// only ties v2 on the 138-token joint attention (71 us) and loses on the shorter windows, so it stays opt-in.
 static int attention_variant() {
     const char* e = getenv("GD_ATTN");
     if (e && e[0] == 'v' && e[1] >= '1' && e[1] <= '3') return e[1] - '0';
@@ -672,7 +672,7 @@ static int run_attention(const gd_attn_desc* d, bool fp32_in, void* stream) {
     // bf16 rows whose segments fit a TMA box go to the persistent TMA-fed kernel
     const int variant = attention_variant();
     if (!fp32_in && variant == 3 && d->d_k == 64 && p.q_rows[0] <= 256 && p.q_rows[1] <= 256 && p.kv_rows[0] <= 256 &&
-        p.kv_rows[1] <= 256 && p.Lq <= 144)
+        p.kv_rows[1] <= 256 && p.Lq <= 144 && attention_tc_smem_bytes(p) <= 232448)
         return launch_attention_tc(p, d->n_clips, s);
     const bool tma_ok = !fp32_in && variant >= 2 && p.q_rows[0] <= 256 && p.q_rows[1] <= 256 &&
                         p.Lq <= 256 && (64 % d->d_k) == 0 && d->heads % (64 / d->d_k) == 0;

@@ -31,7 +31,8 @@ __device__ __forceinline__ float ex2_approx(float x) {  // MUFU.EX2; -inf -> 0, 
 
 // row-major bf16 tensor map with a [box_rows x 64-column] box, no swizzle (attention.cu)
 int make_rows_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
-// tcgen05 attention for d_k = 64 (attention_tc.cu); returns GD_OK or an error
+// tcgen05 attention for d_k = 64, software-pipelined over items (attention_tc.cu); returns GD_OK or an error
 int launch_attention_tc(const AttnParams& p, int n_clips, cudaStream_t s);
+size_t attention_tc_smem_bytes(const AttnParams& p);  // shared memory it needs for this shape (one CTA per SM)
 
 }  // namespace gd

@@ -1,39 +1,33 @@
-// MultiDConvHeadAttention core on the 5th-generation tensor cores (d_k = 64, bf16 rows): tcgen05.mma for S = Q·Kᵀ and
-// O = P·V with the accumulators in TMEM, one thread per query row for the softmax.
+// MultiDConvHeadAttention core on the 5th-generation tensor cores (d_k = 64, bf16 rows, <= 144 queries, <= 160 keys):
+// tcgen05.mma for S = Q·Kᵀ and O = P·V with the accumulators in TMEM, one thread per query row for the softmax, and a
+// warp-specialised software pipeline over the work items (clip, head) - opt-in with GD_ATTN=v3.
 //
-// Work item = (clip, head), persistent CTAs of 9 warps, two per SM.  Per item:
-//   TMA      raw Q/K/V row blocks -> shared memory (dense 128-B rows, [zero | L tokens | zero] per tensor)
-//   conv     depth-wise conv3 over tokens (fp32 FMA): Q, K -> K-major SWIZZLE_128B operand tiles, V -> Vᵀ tile (d_k rows,
-//            keys contiguous) so that both MMAs take plain K-major descriptors
-//   S        one thread issues 4 x tcgen05.mma (M = 128 query rows, N = keys padded to 16, K = 16) -> TMEM
-//   softmax  a thread owns TMEM lane r = query row r (warps w and w+4 split the keys of quadrant w&3): two sweeps of
-//            tcgen05.ld (row max, then exp / sum), partial results meet in spare TMEM columns; no shuffles, no ldmatrix,
-//            no per-warp MMA fragments; P goes to shared memory as the bf16 A operand
-//   O        keys/16 x tcgen05.mma (N = 64) -> TMEM; the row's thread scales by 1/sum, a swizzled staging tile makes the
-//            global stores full 128-B rows
-// The raw blocks are dead after the conv and the P tile is needed only between the two MMAs, so P aliases the raw
-// region (115 KB per CTA for the 138-token joint attention instead of 164 KB: that is what keeps two CTAs on an SM);
-// the next item's TMA load is issued as soon as the last P·V has retired.
-// Status: numerically validated against the fp32 reference (tests/test_kernels_gpu.py, GD_ATTN=v3) but NOT the default.
-// Measured on B200, 256 clips x 8 heads per launch (v2 = mma.sync kernel in attention.cu):
-//     pose 34 tokens 36 us (v2 21), memory 104 tokens 61 us (v2 49), joint 138 tokens 75 us (v2 74), 34x138 59 us (v2 41)
-// The matrix products cost nothing here, but an item is a chain of dependent latencies - TMA, conv, MMA, TMEM loads,
-// shared-memory P, MMA, TMEM loads - with three CTA-wide barriers, and at 34..138 tokens there is too little work per
-// item to hide it with two CTAs per SM (ncu: 2.3-6.3 barrier-stall cycles per issued instruction).  Next step for this
-// kernel: several items in flight per CTA (conv'd operand tiles double-buffered, P kept in TMEM as the A operand).
+// One CTA per SM, 16 warps, three concurrent stages connected by mbarriers, so that the latency chain of an item
+// (TMA -> conv -> MMA -> softmax -> MMA -> epilogue) overlaps with its neighbours':
+//   conv warps 8..13(+15)  raw(i) -> operand tiles cv[i&1]: depth-wise conv3 over tokens (fp32 FMA); Q, K -> K-major
+//                          SWIZZLE_128B tiles, V -> Vᵀ tile (d_k rows, keys contiguous) so that both MMAs take plain
+//                          K-major descriptors; then the TMA load of raw(i+1) is issued
+//   control thread (w14)   S[i&1] = Q Kᵀ as soon as cv[i&1] is complete - one item ahead of the softmax -, O[i&1] = P V as
+//                          soon as P(i) is complete; tcgen05.commit hands buffers back (cv, P) and on (S, O)
+//   softmax warps 0..7     thread = TMEM lane = query row (warps w / w+4 split the keys and the output columns; partial
+//                          row max / sum meet in spare TMEM columns): two sweeps of tcgen05.ld over S, P -> shared memory
+//                          as the bf16 A operand; later O -> scaled by 1/sum -> 64-byte row segments to global
+//   tail warp 15           query rows 128..143 (the 138-token joint attention has ten) with mma.sync from cv[i&1], instead of
+//                          a second, almost empty 128-row tensor-core tile
+// Shared memory: raw 54 KB + 2 x 61 KB operand tiles + 48 KB P = 221 KB for the joint attention; TMEM: S and O
+// double-buffered (2 x 160 + 2 x 64 columns) + 8 exchange columns.
+//
+// Status: validated against the fp32 reference (tests/test_kernels_gpu.py) but NOT the default.  B200, 256 clips x 8
+// heads per launch (v2 = mma.sync kernel in attention.cu): pose 34 tokens 33 us (v2 21), memory 104 tokens 52 us (v2 47),
+// joint 138 tokens 71 us (v2 71), 34x138 52 us (v2 38).  The matrix products are free here, but per item the conv
+// (~6.8 k warp-instructions) and the softmax sweeps (~5.6 k) cost as much as the whole mma.sync kernel (13.7 k), the
+// single raw buffer exposes one TMA round trip per item on the conv stage, and at 34..138 tokens the fixed per-item
+// latencies dominate.  What would make it win: P kept in TMEM as the A operand (frees 48 KB for a second raw buffer),
+// packed bf16 conv arithmetic, several heads per 128-row tile for the short windows.
 #include "attention_common.cuh"
 
 namespace gd {
 
-struct TcGeom {
-    int n_items, Lq16, Lk16, n_tiles, kblocks;
-    int raw_k_off, raw_v_off, raw_bytes;     // packed raw blocks, rows of 128 B
-    int cvq_off, cvk_off, vt_off, bar_off;   // operand tiles (1024-B aligned), barriers
-    uint32_t tx_bytes, tmem_cols, o_col, x_col;  // x_col: four spare TMEM columns for the row max / sum exchange
-};
-
-constexpr int TC_THREADS = 288;   // 8 warps for the tcgen05 tile + warp 8 for query rows 128..143 (mma.sync)
-constexpr int TC_MMA_THREAD = 128;  // warp 4, lane 0
 
 __device__ __forceinline__ void tmem_alloc_dyn(uint32_t* smem_result, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_result)), "r"(cols)
@@ -99,40 +93,43 @@ __device__ __forceinline__ void conv16_rows(const uint8_t* src, uint8_t* dst, in
     }
 }
 
-__device__ __forceinline__ float bf16_lane(const uint2& u, int i) {  // i-th of the four bf16 packed in u
-    const uint32_t w = (i < 2) ? u.x : u.y;
-    return __uint_as_float((i & 1) ? (w & 0xffff0000u) : (w << 16));
-}
-
 // conv3 of 16 tokens x 4 channels written TRANSPOSED: Vᵀ tile, row = channel, 16 consecutive keys = two 16-B chunks of
 // key block p0/64.  Keys >= Lk are written as zeros (their P is zero; this keeps 0 * x finite).
 __device__ __forceinline__ void conv16_vt(const uint8_t* src, uint8_t* vt, int p0, int c, int Lk, const Taps4& t) {
     uint2 raw[18];
 #pragma unroll
     for (int s = 0; s < 18; ++s) raw[s] = *reinterpret_cast<const uint2*>(src + s * ATT_ROW_BYTES);
-    const float w0[4] = {t.w0.x, t.w0.y, t.w0.z, t.w0.w}, w1[4] = {t.w1.x, t.w1.y, t.w1.z, t.w1.w};
-    const float w2[4] = {t.w2.x, t.w2.y, t.w2.z, t.w2.w}, bb[4] = {t.b.x, t.b.y, t.b.z, t.b.w};
+    uint32_t w[4][8];  // per channel: eight bf16x2 words = sixteen consecutive keys
+    float4 prev = unpack_bf16x4(raw[0]), cur = unpack_bf16x4(raw[1]);
+    float4 even = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        const float4 nxt = unpack_bf16x4(raw[s + 2]);
+        float4 r;
+        r.x = fmaf(t.w0.x, prev.x, fmaf(t.w1.x, cur.x, fmaf(t.w2.x, nxt.x, t.b.x)));
+        r.y = fmaf(t.w0.y, prev.y, fmaf(t.w1.y, cur.y, fmaf(t.w2.y, nxt.y, t.b.y)));
+        r.z = fmaf(t.w0.z, prev.z, fmaf(t.w1.z, cur.z, fmaf(t.w2.z, nxt.z, t.b.z)));
+        r.w = fmaf(t.w0.w, prev.w, fmaf(t.w1.w, cur.w, fmaf(t.w2.w, nxt.w, t.b.w)));
+        if (p0 + s >= Lk) r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s & 1) {
+            w[0][s >> 1] = pack_bf16x2(even.x, r.x);
+            w[1][s >> 1] = pack_bf16x2(even.y, r.y);
+            w[2][s >> 1] = pack_bf16x2(even.z, r.z);
+            w[3][s >> 1] = pack_bf16x2(even.w, r.w);
+        } else {
+            even = r;
+        }
+        prev = cur;
+        cur = nxt;
+    }
     uint8_t* blk = vt + (p0 >> 6) * 8192;
     const int ch0 = (p0 & 63) >> 3;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        float r[16];
-#pragma unroll
-        for (int s = 0; s < 16; ++s) {
-            r[s] = fmaf(w0[i], bf16_lane(raw[s], i), fmaf(w1[i], bf16_lane(raw[s + 1], i), fmaf(w2[i], bf16_lane(raw[s + 2], i), bb[i])));
-            if (p0 + s >= Lk) r[s] = 0.f;
-        }
         const int row = c + i;
         uint8_t* rp = blk + row * ATT_ROW_BYTES;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            uint4 o;
-            o.x = pack_bf16x2(r[8 * h + 0], r[8 * h + 1]);
-            o.y = pack_bf16x2(r[8 * h + 2], r[8 * h + 3]);
-            o.z = pack_bf16x2(r[8 * h + 4], r[8 * h + 5]);
-            o.w = pack_bf16x2(r[8 * h + 6], r[8 * h + 7]);
-            *reinterpret_cast<uint4*>(rp + (((ch0 + h) ^ (row & 7)) << 4)) = o;
-        }
+        *reinterpret_cast<uint4*>(rp + ((ch0 ^ (row & 7)) << 4)) = make_uint4(w[i][0], w[i][1], w[i][2], w[i][3]);
+        *reinterpret_cast<uint4*>(rp + (((ch0 + 1) ^ (row & 7)) << 4)) = make_uint4(w[i][4], w[i][5], w[i][6], w[i][7]);
     }
 }
 
@@ -228,207 +225,272 @@ __device__ __forceinline__ void tail_rows_mma_sync(const uint8_t* cvq, const uin
     }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 2)
+struct TcpGeom {
+    int n_items, Lq16, Lk16, kblocks;
+    int raw_k_off, raw_v_off, raw_bytes;
+    int cv_off, cv_stride, cvk_rel, vt_rel;  // operand tile set b at cv_off + b * cv_stride: [cvq | cvk | vt]
+    int p_off, bar_off;
+    uint32_t tx_bytes;
+};
+constexpr int TCP_THREADS = 512;
+constexpr int TCP_CONV_WARPS = 6;
+constexpr uint32_t TCP_S_COL = 0, TCP_S_STRIDE = 160, TCP_O_COL = 320, TCP_O_STRIDE = 64, TCP_X_COL = 448;
+
+
+__global__ void __launch_bounds__(TCP_THREADS, 1)
 dconv_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q0, const __grid_constant__ CUtensorMap tm_q1,
-                          const __grid_constant__ CUtensorMap tm_k0, const __grid_constant__ CUtensorMap tm_k1,
-                          const __grid_constant__ CUtensorMap tm_v0, const __grid_constant__ CUtensorMap tm_v1,
-                          const AttnParams p, const TcGeom g) {
+                           const __grid_constant__ CUtensorMap tm_k0, const __grid_constant__ CUtensorMap tm_k1,
+                           const __grid_constant__ CUtensorMap tm_v0, const __grid_constant__ CUtensorMap tm_v1,
+                           const AttnParams p, const TcpGeom g) {
     extern __shared__ __align__(1024) uint8_t smem_tc[];
     uint8_t* smem = smem_tc;
     uint8_t* raw_q = smem;
     uint8_t* raw_k = smem + g.raw_k_off;
     uint8_t* raw_v = smem + g.raw_v_off;
-    uint8_t* pbuf = smem;  // P (and the staging tile of non-final query tiles) alias the raw blocks
-    uint8_t* cvq = smem + g.cvq_off;
-    uint8_t* cvk = smem + g.cvk_off;
-    uint8_t* vt = smem + g.vt_off;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + g.bar_off);
-    uint64_t* mma_bar = full_bar + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+    uint8_t* pbuf = smem + g.p_off;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.bar_off);
+    uint64_t* raw_full = bars;          // TMA -> conv warps  (bars[1], bars[2] unused)
+    uint64_t* cv_full = bars + 3;       // [2] conv warps -> control, tail
+    uint64_t* cv_empty = bars + 5;      // [2] P·V retired (+ tail warp done) -> conv warps
+    uint64_t* s_full = bars + 7;        // [2] Q·Kᵀ retired -> softmax warps
+    uint64_t* s_empty = bars + 9;       // [2] softmax warps have read S -> control
+    uint64_t* p_full = bars + 11;       // softmax warps wrote P -> control
+    uint64_t* p_empty = bars + 12;      // P·V retired -> softmax warps
+    uint64_t* o_full = bars + 13;       // [2] P·V retired -> softmax warps
+    uint64_t* o_empty = bars + 15;      // [2] softmax warps have read O -> control
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Lq = p.Lq, Lk = p.Lk;
+    const bool has_tail = Lq > 128;
+    const int n_conv_warps = has_tail ? TCP_CONV_WARPS : TCP_CONV_WARPS + 1;  // warp 15 convolves when there are no tail rows
 
     if (tid == 0) {
-        if (smem_u32(smem) & 1023) __trap();  // the swizzled operand tiles rely on a 1024-B aligned base
+        if (smem_u32(smem) & 1023) __trap();
         prefetch_tensormap(&tm_q0), prefetch_tensormap(&tm_k0), prefetch_tensormap(&tm_v0);
         if (p.q_rows[1]) prefetch_tensormap(&tm_q1);
         if (p.kv_rows[1]) prefetch_tensormap(&tm_k1), prefetch_tensormap(&tm_v1);
-        mbar_init(full_bar, 1);
-        mbar_init(mma_bar, 1);
+        mbar_init(raw_full, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&cv_full[b], n_conv_warps);
+            mbar_init(&cv_empty[b], has_tail ? 2 : 1);
+            mbar_init(&s_full[b], 1);
+            mbar_init(&s_empty[b], 8);
+            mbar_init(&o_full[b], 1);
+            mbar_init(&o_empty[b], 8);
+        }
+        mbar_init(p_full, 8);
+        mbar_init(p_empty, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc_dyn(tmem_slot, g.tmem_cols);
-    for (int i = tid; i < g.raw_bytes / 16; i += TC_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (warp == 1) tmem_alloc_dyn(tmem_slot, 512);
+    for (int i = tid; i < g.raw_bytes / 16; i += TCP_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
     tc_fence_before_sync();
     pdl_launch_dependents();
-    pdl_wait();  // set-up touched only shared memory / TMEM; Q/K/V come from the previous kernel
+    pdl_wait();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
+    const int nsq = g.Lq16 / 16, nsk = g.Lk16 / 16;
+    const float c_log2 = p.scale_log2;
+    const int n_mine = (g.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // items of this CTA
+
     auto issue_load = [&](int item) {  // one thread; token rows start at row 1 of each raw block
         const int clip = item / p.heads, col0 = (item % p.heads) * 64;
-        mbar_arrive_expect_tx(full_bar, g.tx_bytes);
-        tma_load_2d(raw_q + ATT_ROW_BYTES, &tm_q0, full_bar, col0, clip * p.q_rows[0]);
-        if (p.q_rows[1]) tma_load_2d(raw_q + (1 + p.q_rows[0]) * ATT_ROW_BYTES, &tm_q1, full_bar, col0, clip * p.q_rows[1]);
-        tma_load_2d(raw_k + ATT_ROW_BYTES, &tm_k0, full_bar, col0, clip * p.kv_rows[0]);
-        tma_load_2d(raw_v + ATT_ROW_BYTES, &tm_v0, full_bar, col0, clip * p.kv_rows[0]);
+        mbar_arrive_expect_tx(raw_full, g.tx_bytes);
+        tma_load_2d(raw_q + ATT_ROW_BYTES, &tm_q0, raw_full, col0, clip * p.q_rows[0]);
+        if (p.q_rows[1]) tma_load_2d(raw_q + (1 + p.q_rows[0]) * ATT_ROW_BYTES, &tm_q1, raw_full, col0, clip * p.q_rows[1]);
+        tma_load_2d(raw_k + ATT_ROW_BYTES, &tm_k0, raw_full, col0, clip * p.kv_rows[0]);
+        tma_load_2d(raw_v + ATT_ROW_BYTES, &tm_v0, raw_full, col0, clip * p.kv_rows[0]);
         if (p.kv_rows[1]) {
-            tma_load_2d(raw_k + (1 + p.kv_rows[0]) * ATT_ROW_BYTES, &tm_k1, full_bar, col0, clip * p.kv_rows[1]);
-            tma_load_2d(raw_v + (1 + p.kv_rows[0]) * ATT_ROW_BYTES, &tm_v1, full_bar, col0, clip * p.kv_rows[1]);
+            tma_load_2d(raw_k + (1 + p.kv_rows[0]) * ATT_ROW_BYTES, &tm_k1, raw_full, col0, clip * p.kv_rows[1]);
+            tma_load_2d(raw_v + (1 + p.kv_rows[0]) * ATT_ROW_BYTES, &tm_v1, raw_full, col0, clip * p.kv_rows[1]);
         }
     };
 
-    int item = blockIdx.x;
-    if (tid == 0 && item < g.n_items) issue_load(item);
-    uint32_t lphase = 0, mphase = 0;
-    const uint32_t idesc_qk = umma_idesc_bf16(128, g.Lk16), idesc_pv = umma_idesc_bf16(128, 64);
-    const int nsq = g.Lq16 / 16, nsk = g.Lk16 / 16;
-    const int units = (nsq + 2 * nsk) * 16;
-    const float c_log2 = p.scale_log2;
-
-    for (; item < g.n_items; item += gridDim.x) {
-        const int clip = item / p.heads, head = item % p.heads;
-        mbar_wait(full_bar, lphase);
-        lphase ^= 1;
-        // ---------------- depth-wise conv3 over tokens, raw -> operand tiles
-        for (int it = tid; it < units; it += TC_THREADS) {
-            const int hc4 = it & 15, sg = it >> 4;
-            const int which = sg < nsq ? 0 : (sg < nsq + nsk ? 1 : 2);
-            const int p0 = (sg - (which == 0 ? 0 : (which == 1 ? nsq : nsq + nsk))) * 16;
-            const Taps4 t = load_taps4(which == 0 ? p.wq : (which == 1 ? p.wk : p.wv),
-                                       which == 0 ? p.bq : (which == 1 ? p.bk : p.bv), hc4 * 4);
-            const uint8_t* src = (which == 0 ? raw_q : (which == 1 ? raw_k : raw_v)) + p0 * ATT_ROW_BYTES + hc4 * 8;
-            if (which == 2)
-                conv16_vt(src, vt, p0, hc4 * 4, Lk, t);
-            else
-                conv16_rows(src, (which == 0 ? cvq : cvk) + p0 * ATT_ROW_BYTES + (hc4 & 1) * 8, hc4 >> 1, t);
+    if ((warp >= 8 && warp < 8 + TCP_CONV_WARPS) || (warp == 15 && !has_tail)) {
+        // ------------------------------------------------------------------ conv warps
+        const int cw = warp == 15 ? TCP_CONV_WARPS : warp - 8;
+        const int ctid = cw * 32 + lane, cthreads = n_conv_warps * 32;
+        const int units = (nsq + 2 * nsk) * 16;
+        if (ctid == 0 && n_mine > 0) issue_load(blockIdx.x);
+        for (int k = 0; k < n_mine; ++k) {
+            const int b = k & 1;
+            const uint32_t ph2 = (k >> 1) & 1;
+            uint8_t* cvq = smem + g.cv_off + b * g.cv_stride;
+            uint8_t* cvk = cvq + g.cvk_rel;
+            uint8_t* vt = cvq + g.vt_rel;
+            mbar_wait(raw_full, k & 1);
+            mbar_wait(&cv_empty[b], ph2 ^ 1);  // the MMAs (and the tail warp) of item k-2 are done with this tile set
+            for (int it = ctid; it < units; it += cthreads) {
+                const int hc4 = it & 15, sg = it >> 4;
+                const int which = sg < nsq ? 0 : (sg < nsq + nsk ? 1 : 2);
+                const int p0 = (sg - (which == 0 ? 0 : (which == 1 ? nsq : nsq + nsk))) * 16;
+                const Taps4 t = load_taps4(which == 0 ? p.wq : (which == 1 ? p.wk : p.wv),
+                                           which == 0 ? p.bq : (which == 1 ? p.bk : p.bv), hc4 * 4);
+                const uint8_t* src = (which == 0 ? raw_q : (which == 1 ? raw_k : raw_v)) + p0 * ATT_ROW_BYTES + hc4 * 8;
+                if (which == 2)
+                    conv16_vt(src, vt, p0, hc4 * 4, Lk, t);
+                else
+                    conv16_rows(src, (which == 0 ? cvq : cvk) + p0 * ATT_ROW_BYTES + (hc4 & 1) * 8, hc4 >> 1, t);
+            }
+            fence_proxy_async();  // ordinary stores -> visible to the tensor core's async-proxy reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&cv_full[b]);
+            asm volatile("bar.sync 2, %0;\n" ::"r"(cthreads) : "memory");  // every conv warp has finished reading raw
+            if (ctid == 0 && k + 1 < n_mine) issue_load(blockIdx.x + (k + 1) * gridDim.x);
         }
-        fence_proxy_async();  // operand tiles were written by ordinary stores; the tensor core reads them through the async proxy
-        __syncthreads();
-
-        // Eight warps share the 128 rows of the tensor-core tile: warp w and w + 4 both own TMEM lane quadrant w & 3 (query
-        // rows 32(w&3)..+31); warp w < 4 takes the first half of the 16-key chunks / of the output columns, warp w + 4 the
-        // second; the two partial row maxima and sums meet in four spare TMEM columns.  Warp 8 does rows 128..143.
+    } else if (warp == 14) {
+        // ------------------------------------------------------------------ control thread: both matrix products
+        if (lane == 0) {
+            const uint32_t idesc_qk = umma_idesc_bf16(128, g.Lk16), idesc_pv = umma_idesc_bf16(128, 64);
+            auto issue_qk = [&](int k) {
+                const int b = k & 1;
+                const uint32_t ph2 = (k >> 1) & 1;
+                uint8_t* cvq = smem + g.cv_off + b * g.cv_stride;
+                mbar_wait(&cv_full[b], ph2);
+                mbar_wait(&s_empty[b], ph2 ^ 1);
+                tc_fence_after_sync();
+                const uint64_t da = umma_desc_k_sw128(smem_u32(cvq));
+                const uint64_t db = umma_desc_k_sw128(smem_u32(cvq + g.cvk_rel));
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16_ss(tmem_base + TCP_S_COL + b * TCP_S_STRIDE, da + 2 * kk, db + 2 * kk, idesc_qk, kk != 0 ? 1u : 0u);
+                umma_commit(&s_full[b]);
+            };
+            if (n_mine > 0) issue_qk(0);
+            for (int k = 0; k < n_mine; ++k) {
+                const int b = k & 1;
+                const uint32_t ph2 = (k >> 1) & 1;
+                if (k + 1 < n_mine) issue_qk(k + 1);  // keeps the softmax warps one item ahead of P·V
+                uint8_t* vt = smem + g.cv_off + b * g.cv_stride + g.vt_rel;
+                mbar_wait(p_full, k & 1);
+                mbar_wait(&o_empty[b], ph2 ^ 1);
+                tc_fence_after_sync();
+                for (int ks = 0; ks < nsk; ++ks) {
+                    const uint64_t da = umma_desc_k_sw128(smem_u32(pbuf + (ks >> 2) * 16384)) + 2 * (ks & 3);
+                    const uint64_t db = umma_desc_k_sw128(smem_u32(vt + (ks >> 2) * 8192)) + 2 * (ks & 3);
+                    umma_bf16_ss(tmem_base + TCP_O_COL + b * TCP_O_STRIDE, da, db, idesc_pv, ks != 0 ? 1u : 0u);
+                }
+                umma_commit(&o_full[b]);   // each commit fires once every MMA issued so far has retired
+                umma_commit(p_empty);
+                umma_commit(&cv_empty[b]);
+            }
+        }
+    } else if (warp == 15) {
+        // ------------------------------------------------------------------ tail warp: query rows 128..143
+        {
+            for (int k = 0; k < n_mine; ++k) {
+                const int b = k & 1;
+                const int item = blockIdx.x + k * gridDim.x;
+                uint8_t* cvq = smem + g.cv_off + b * g.cv_stride;
+                mbar_wait(&cv_full[b], (k >> 1) & 1);
+                tail_rows_mma_sync(cvq, cvq + g.cvk_rel, cvq + g.vt_rel, nsk, Lq, Lk, c_log2, lane, p, item / p.heads, item % p.heads);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&cv_empty[b]);
+            }
+        }
+    } else if (warp < 8) {
+        // ------------------------------------------------------------------ softmax / output warps
         const int rows_valid = min(128, Lq);
-        const int quad = warp & 3, khalf = (warp >> 2) & 1;
-        const bool active = warp < 8 && quad * 32 < rows_valid;
-        const int row = quad * 32 + lane;  // TMEM lane = query row
+        const int quad = warp & 3, khalf = warp >> 2;
+        const int row = quad * 32 + lane;
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
         const int c_split = (nsk + 1) >> 1;
         const int c_lo = khalf ? c_split : 0, c_hi = khalf ? nsk : c_split;
-        // ---------------- S = Q Kᵀ (rows 0..127)
-        if (tid == TC_MMA_THREAD) {
+        const bool active = quad * 32 < rows_valid;  // warps without valid rows still take part in every barrier
+        for (int k = 0; k < n_mine; ++k) {
+            const int b = k & 1;
+            const uint32_t ph2 = (k >> 1) & 1;
+            const int item = blockIdx.x + k * gridDim.x;
+            const int clip = item / p.heads, head = item % p.heads;
+            const uint32_t s_addr = t_lane + TCP_S_COL + b * TCP_S_STRIDE;
+            const uint32_t x_addr = t_lane + TCP_X_COL + b * 4;
+            mbar_wait(&s_full[b], ph2);
             tc_fence_after_sync();
-            const uint64_t da = umma_desc_k_sw128(smem_u32(cvq));
-            const uint64_t db = umma_desc_k_sw128(smem_u32(cvk));
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
-            umma_commit(mma_bar);
-        }
-        __syncwarp();
-        if (warp == 8 && Lq > 128) tail_rows_mma_sync(cvq, cvk, vt, nsk, Lq, Lk, c_log2, lane, p, clip, head);
-        if (active) {
-            mbar_wait(mma_bar, mphase);
-            tc_fence_after_sync();
-            // sweep 1: maximum over this thread's share of the valid keys
             float m = -INFINITY;
-            for (int c = c_lo; c < c_hi; ++c) {
-                uint32_t v[16];
-                tmem_ld_32x32b_x16(t_lane + c * 16, v);
-                tmem_ld_wait();
-                if (c * 16 + 16 <= Lk) {
+            if (active) {
+                for (int c = c_lo; c < c_hi; ++c) {
+                    uint32_t v[16];
+                    tmem_ld_32x32b_x16(s_addr + c * 16, v);
+                    tmem_ld_wait();
+                    if (c * 16 + 16 <= Lk) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(v[j]));
-                } else {
-                    const int nvalid = Lk - c * 16;
+                        for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+                    } else {
+                        const int nvalid = Lk - c * 16;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (j < nvalid) m = fmaxf(m, __uint_as_float(v[j]));
+                        for (int j = 0; j < 16; ++j)
+                            if (j < nvalid) m = fmaxf(m, __uint_as_float(v[j]));
+                    }
                 }
             }
-            tmem_st_32x32b_x1(t_lane + g.x_col + khalf, m);
+            tmem_st_32x32b_x1(x_addr + khalf, m);
             tmem_st_wait_tc();
             tc_fence_before_sync();
-        }
-        mphase ^= 1;
-        if (warp < 8) softmax_warps_sync();  // partial maxima published (the tail warp is not part of this barrier)
-        if (active) {
+            softmax_warps_sync();  // both halves of every row have published their maximum
             tc_fence_after_sync();
-            const float m = fmaxf(tmem_ld_32x32b_x1(t_lane + g.x_col), tmem_ld_32x32b_x1(t_lane + g.x_col + 1));
+            const float max_a = tmem_ld_32x32b_x1(x_addr), max_b = tmem_ld_32x32b_x1(x_addr + 1);
             tmem_ld_wait();
-            // sweep 2: p = exp2(s*c - m*c), row sum, P -> shared memory (bf16, K-major SWIZZLE_128B, 64 keys per block)
-            const float mo = m * c_log2;
+            m = fmaxf(max_a, max_b);
+            mbar_wait(p_empty, (k & 1) ^ 1);  // P·V of the previous item has retired: the P tile may be overwritten
             float part_sum = 0.f;
-            uint8_t* prow = pbuf + row * ATT_ROW_BYTES;
-            for (int c = c_lo; c < c_hi; ++c) {
-                uint32_t v[16];
-                tmem_ld_32x32b_x16(t_lane + c * 16, v);
-                tmem_ld_wait();
-                float e[16];
-                if (c * 16 + 16 <= Lk) {
+            if (active) {
+                const float mo = m * c_log2;
+                uint8_t* prow = pbuf + row * ATT_ROW_BYTES;
+                for (int c = c_lo; c < c_hi; ++c) {
+                    uint32_t v[16];
+                    tmem_ld_32x32b_x16(s_addr + c * 16, v);
+                    tmem_ld_wait();
+                    float e[16];
+                    if (c * 16 + 16 <= Lk) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) e[j] = ex2_approx(fmaf(__uint_as_float(v[j]), c_log2, -mo));
-                } else {
-                    const int nvalid = Lk - c * 16;
+                        for (int j = 0; j < 16; ++j) e[j] = ex2_approx(fmaf(__uint_as_float(v[j]), c_log2, -mo));
+                    } else {
+                        const int nvalid = Lk - c * 16;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) e[j] = j < nvalid ? ex2_approx(fmaf(__uint_as_float(v[j]), c_log2, -mo)) : 0.f;
-                }
+                        for (int j = 0; j < 16; ++j) e[j] = j < nvalid ? ex2_approx(fmaf(__uint_as_float(v[j]), c_log2, -mo)) : 0.f;
+                    }
 #pragma unroll
-                for (int j = 0; j < 16; ++j) part_sum += e[j];
-                uint8_t* blk = prow + (c >> 2) * 16384;
-                const int cc = (c & 3) * 2;
+                    for (int j = 0; j < 16; ++j) part_sum += e[j];
+                    uint8_t* blk = prow + (c >> 2) * 16384;
+                    const int cc = (c & 3) * 2;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint4 o;
-                    o.x = pack_bf16x2(e[8 * h + 0], e[8 * h + 1]);
-                    o.y = pack_bf16x2(e[8 * h + 2], e[8 * h + 3]);
-                    o.z = pack_bf16x2(e[8 * h + 4], e[8 * h + 5]);
-                    o.w = pack_bf16x2(e[8 * h + 6], e[8 * h + 7]);
-                    *reinterpret_cast<uint4*>(blk + (((cc + h) ^ (row & 7)) << 4)) = o;
+                    for (int h = 0; h < 2; ++h) {
+                        uint4 o;
+                        o.x = pack_bf16x2(e[8 * h + 0], e[8 * h + 1]);
+                        o.y = pack_bf16x2(e[8 * h + 2], e[8 * h + 3]);
+                        o.z = pack_bf16x2(e[8 * h + 4], e[8 * h + 5]);
+                        o.w = pack_bf16x2(e[8 * h + 6], e[8 * h + 7]);
+                        *reinterpret_cast<uint4*>(blk + (((cc + h) ^ (row & 7)) << 4)) = o;
+                    }
                 }
             }
-            tmem_st_32x32b_x1(t_lane + g.x_col + 2 + khalf, part_sum);
+            tmem_st_32x32b_x1(x_addr + 2 + khalf, part_sum);
             tmem_st_wait_tc();
             fence_proxy_async();
             tc_fence_before_sync();
-        }
-        if (warp < 8) softmax_warps_sync();  // P complete, every read of S retired, partial sums published
-        // ---------------- O = P V
-        if (tid == TC_MMA_THREAD) {
-            tc_fence_after_sync();
-            for (int ks = 0; ks < nsk; ++ks) {
-                const uint64_t da = umma_desc_k_sw128(smem_u32(pbuf + (ks >> 2) * 16384)) + 2 * (ks & 3);
-                const uint64_t db = umma_desc_k_sw128(smem_u32(vt + (ks >> 2) * 8192)) + 2 * (ks & 3);
-                umma_bf16_ss(tmem_base + g.o_col, da, db, idesc_pv, ks != 0 ? 1u : 0u);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&s_empty[b]);
+                mbar_arrive(p_full);
             }
-            umma_commit(mma_bar);
-        }
-        __syncwarp();
-        if (active) {
-            mbar_wait(mma_bar, mphase);
+            // ---- output: O[b] is complete once P·V has retired
+            mbar_wait(&o_full[b], ph2);
             tc_fence_after_sync();
-            if (warp == 0) {
-                // P is dead (its MMA has retired): restore the zero padding rows it covered, then fetch the next item
-                const int zr[6] = {0, Lq + 1, 0, Lk + 1, 0, Lk + 1};
-                uint8_t* const zb[6] = {raw_q, raw_q, raw_k, raw_k, raw_v, raw_v};
-                for (int i = lane; i < 48; i += 32)
-                    *reinterpret_cast<uint4*>(zb[i >> 3] + zr[i >> 3] * ATT_ROW_BYTES + (i & 7) * 16) = make_uint4(0, 0, 0, 0);
-                __syncwarp();
-                if (lane == 0 && item + (int)gridDim.x < g.n_items) issue_load(item + gridDim.x);
-            }
-            const float inv_sum = 1.0f / (tmem_ld_32x32b_x1(t_lane + g.x_col + 2) + tmem_ld_32x32b_x1(t_lane + g.x_col + 3));
-            // this thread's 32 of the row's 64 output columns: 64 contiguous bytes = two full 32-B sectors
+            const float sum_a = tmem_ld_32x32b_x1(x_addr + 2), sum_b = tmem_ld_32x32b_x1(x_addr + 3);
+            tmem_ld_wait();
+            const float inv_sum = 1.0f / (sum_a + sum_b);
             __nv_bfloat16* orow = nullptr;
-            if (row < rows_valid)
+            if (active && row < rows_valid)
                 orow = ((row < p.q_rows[0]) ? p.out[0] + ((size_t)clip * p.q_rows[0] + row) * p.out_ld[0]
                                             : p.out[1] + ((size_t)clip * p.q_rows[1] + (row - p.q_rows[0])) * p.out_ld[1]) +
                        head * 64 + khalf * 32;
 #pragma unroll
             for (int c2 = 0; c2 < 2; ++c2) {
                 uint32_t v[16];
-                tmem_ld_32x32b_x16(t_lane + g.o_col + (khalf * 2 + c2) * 16, v);
+                tmem_ld_32x32b_x16(t_lane + TCP_O_COL + b * TCP_O_STRIDE + (khalf * 2 + c2) * 16, v);
                 tmem_ld_wait();
                 if (orow) {
 #pragma unroll
@@ -443,48 +505,43 @@ dconv_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q0, const __gri
                 }
             }
             tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&o_empty[b]);
         }
-        mphase ^= 1;
-        __syncthreads();  // operand tiles, S and O are free for the next item
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 1) tmem_dealloc_dyn(tmem_base, g.tmem_cols);
+    if (warp == 1) tmem_dealloc_dyn(tmem_base, 512);
+}
+
+// shared memory the pipelined kernel needs for this shape (it runs one CTA per SM: <= 227 KB)
+size_t attention_tc_smem_bytes(const AttnParams& p) {
+    const int Lq16 = (p.Lq + 15) & ~15, Lk16 = (p.Lk + 15) & ~15, kblocks = (Lk16 + 63) / 64;
+    const int raw = (p.Lq + 2 + 2 * (p.Lk + 2)) * ATT_ROW_BYTES;
+    int cv_stride = (Lq16 + Lk16) * ATT_ROW_BYTES + kblocks * 8192;
+    if (cv_stride < 16384) cv_stride = 16384;
+    return (size_t)((raw + 1023) & ~1023) + 2 * (size_t)cv_stride + (size_t)kblocks * 16384 + 256;
 }
 
 int launch_attention_tc(const AttnParams& p, int n_clips, cudaStream_t s) {
-    TcGeom g{};
+    TcpGeom g{};
     g.n_items = n_clips * p.heads;
     g.Lq16 = (p.Lq + 15) & ~15, g.Lk16 = (p.Lk + 15) & ~15;
-    g.n_tiles = 1;  // rows 0..127 on the tensor cores, rows 128..143 by the mma.sync warp
     g.kblocks = (g.Lk16 + 63) / 64;
-    // raw blocks: [zero | L rows | zero] per tensor, packed; the conv of the last 16-token segment may read up to 15 rows
-    // past a block (finite data of the next block / tile: results land in padded rows that are masked or zeroed)
+    if (g.Lk16 > (int)TCP_S_STRIDE) return set_error(GD_ERR_INVALID, "gd_dconv_attention: more than 160 keys");
     g.raw_k_off = (p.Lq + 2) * ATT_ROW_BYTES;
     g.raw_v_off = g.raw_k_off + (p.Lk + 2) * ATT_ROW_BYTES;
     g.raw_bytes = g.raw_v_off + (p.Lk + 2) * ATT_ROW_BYTES;
-    const int p_bytes = g.kblocks * 16384;
-    int region0 = g.raw_bytes > p_bytes ? g.raw_bytes : p_bytes;
-    region0 = (region0 + 1023) & ~1023;
-    g.cvq_off = region0;
-    g.cvk_off = g.cvq_off + g.Lq16 * ATT_ROW_BYTES;
-    g.vt_off = g.cvk_off + g.Lk16 * ATT_ROW_BYTES;
-    g.bar_off = g.vt_off + g.kblocks * 8192;
-    // every query tile is read as 128 rows (and the last one doubles as a 16-KB staging tile): keep that in bounds
-    if (g.bar_off < g.cvq_off + g.n_tiles * 16384) g.bar_off = g.cvq_off + g.n_tiles * 16384;
+    g.cv_off = (g.raw_bytes + 1023) & ~1023;
+    g.cvk_rel = g.Lq16 * ATT_ROW_BYTES;
+    g.vt_rel = g.cvk_rel + g.Lk16 * ATT_ROW_BYTES;
+    g.cv_stride = g.vt_rel + g.kblocks * 8192;
+    if (g.cv_stride < 16384) g.cv_stride = 16384;  // the query tile is read as 128 rows
+    g.p_off = g.cv_off + 2 * g.cv_stride;
+    g.bar_off = g.p_off + g.kblocks * 16384;
     g.tx_bytes = (uint32_t)(p.Lq + 2 * p.Lk) * ATT_ROW_BYTES;
-    g.o_col = (uint32_t)((g.Lk16 + 31) & ~31);
-    g.x_col = g.o_col + 64;
-    uint32_t cols = 32;
-    while (cols < g.x_col + 4) cols <<= 1;
-    g.tmem_cols = cols;
-    // the mbarriers live in the padding behind the raw blocks when there is room (the 138-token joint attention then
-    // fits two CTAs per SM to the byte: 2 x (115 712 + 1 024) = 233 472)
-    size_t smem = (size_t)g.bar_off + 64;
-    if (region0 - g.raw_bytes >= 64 && g.raw_bytes >= p_bytes) {
-        smem = (size_t)g.bar_off;
-        g.bar_off = g.raw_bytes;
-    }
+    const size_t smem = (size_t)g.bar_off + 256;
+    if (smem > 232448) return set_error(GD_ERR_CUDA, "gd_dconv_attention: pipelined tcgen05 kernel needs %zu B of shared memory", smem);
     if (reinterpret_cast<uintptr_t>(p.wq) & 15 || reinterpret_cast<uintptr_t>(p.wk) & 15 || reinterpret_cast<uintptr_t>(p.wv) & 15 ||
         reinterpret_cast<uintptr_t>(p.bq) & 15 || reinterpret_cast<uintptr_t>(p.bk) & 15 || reinterpret_cast<uintptr_t>(p.bv) & 15)
         return set_error(GD_ERR_INVALID, "gd_dconv_attention: conv taps must be 16-byte aligned");
@@ -505,19 +562,11 @@ int launch_attention_tc(const AttnParams& p, int n_clips, cudaStream_t s) {
     if (smem > configured) {
         GD_CUDA_CHECK(cudaFuncSetAttribute(dconv_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
-        GD_CUDA_CHECK(cudaFuncSetAttribute(dconv_attention_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                           cudaSharedmemCarveoutMaxShared));
         configured = smem;
     }
-    // CTAs per SM: 128 registers x 256 threads -> two by the register file; shared memory (228 KB per SM, 1 KB reserved
-    // per CTA) and TMEM (512 columns per SM) can only lower that
-    int per_sm = 2;  // 96 registers x 288 threads
-    if ((smem + 1024) * 2 > 233472) per_sm = 1;
-    if (per_sm * (int)g.tmem_cols > 512) per_sm = 512 / (int)g.tmem_cols;
-    if (smem + 1024 > 233472) return set_error(GD_ERR_CUDA, "gd_dconv_attention: tcgen05 kernel does not fit on an SM (smem %zu B)", smem);
-    int grid = per_sm * sm_count();
+    int grid = sm_count();
     if (grid > g.n_items) grid = g.n_items;
-    GD_CUDA_CHECK(launch_k(dconv_attention_tc_kernel, grid, TC_THREADS, smem, s, 1, tq[0], tq[1], tk[0], tk[1], tv[0], tv[1], p, g));
+    GD_CUDA_CHECK(launch_k(dconv_attention_tc_kernel, grid, TCP_THREADS, smem, s, 1, tq[0], tq[1], tk[0], tk[1], tv[0], tv[1], p, g));
     count_launch();
     GD_CUDA_CHECK(cudaGetLastError());
     return GD_OK;

@@ -191,7 +191,9 @@ def test_dconv_attention(gd, dk, rows_q, rows_kv, f32, N):
                                                ((7, 0), (7, 0), 3), ((34, 0), (34, 0), 300), ((144, 0), (160, 0), 4), ((129, 0), (17, 0), 3),
                                                ((128, 0), (128, 0), 3)])
 def test_dconv_attention_tcgen05_variant(gd, rows_q, rows_kv, N, monkeypatch):
-    """The opt-in tcgen05/TMEM attention kernel (GD_ATTN=v3, d_k = 64): same reference, one and two 128-row query tiles."""
+    """The opt-in tcgen05/TMEM attention kernel (GD_ATTN=v3, d_k = 64): warp-specialised pipeline over items.  Same reference;
+    shapes with and without the mma.sync tail rows (queries 128..143); the 144x160 case exceeds its shared memory and must
+    fall back to the default kernel."""
     monkeypatch.setenv("GD_ATTN", "v3")
     _dconv_attention_case(gd, 64, rows_q, rows_kv, False, N)
 
