@@ -352,7 +352,31 @@ __device__ __forceinline__ void conv_unit16(const uint8_t* src /* raw row p0 (= 
     }
 }
 
-template <int DK, int KB, int MAXT, int MAXREG>
+// Same unit with packed bf16x2 arithmetic (three HFMA2 per column pair, no unpack / repack): a third of the
+// instructions, at the price of rounding the taps and the two partial sums to bf16.
+__device__ __forceinline__ void conv_unit16_bf16(const uint8_t* src, uint8_t* dst, int chunk, const float* tp) {
+    const float4 w0 = *reinterpret_cast<const float4*>(tp), w1 = *reinterpret_cast<const float4*>(tp + 8);
+    const float4 w2 = *reinterpret_cast<const float4*>(tp + 16), bb = *reinterpret_cast<const float4*>(tp + 24);
+    const __nv_bfloat162 w0a = __floats2bfloat162_rn(w0.x, w0.y), w0b = __floats2bfloat162_rn(w0.z, w0.w);
+    const __nv_bfloat162 w1a = __floats2bfloat162_rn(w1.x, w1.y), w1b = __floats2bfloat162_rn(w1.z, w1.w);
+    const __nv_bfloat162 w2a = __floats2bfloat162_rn(w2.x, w2.y), w2b = __floats2bfloat162_rn(w2.z, w2.w);
+    const __nv_bfloat162 bba = __floats2bfloat162_rn(bb.x, bb.y), bbb = __floats2bfloat162_rn(bb.z, bb.w);
+    uint2 raw[18];
+#pragma unroll
+    for (int s = 0; s < 18; ++s) raw[s] = *reinterpret_cast<const uint2*>(src + s * ATT2_ROW_BYTES);
+    auto b2 = [](uint32_t u) { return *reinterpret_cast<const __nv_bfloat162*>(&u); };
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        const __nv_bfloat162 ra = __hfma2(w0a, b2(raw[s].x), __hfma2(w1a, b2(raw[s + 1].x), __hfma2(w2a, b2(raw[s + 2].x), bba)));
+        const __nv_bfloat162 rb = __hfma2(w0b, b2(raw[s].y), __hfma2(w1b, b2(raw[s + 1].y), __hfma2(w2b, b2(raw[s + 2].y), bbb)));
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&ra);
+        o.y = *reinterpret_cast<const uint32_t*>(&rb);
+        *reinterpret_cast<uint2*>(dst + s * ATT2_ROW_BYTES + ((chunk ^ (s & 7)) << 4)) = o;
+    }
+}
+
+template <int DK, int KB, int MAXT, int MAXREG, bool CONV_BF16>
 __global__ void __launch_bounds__(MAXT) __maxnreg__(MAXREG)
 dconv_attention_tma_kernel(const __grid_constant__ CUtensorMap tm_q0, const __grid_constant__ CUtensorMap tm_q1,
                            const __grid_constant__ CUtensorMap tm_k0, const __grid_constant__ CUtensorMap tm_k1,
@@ -444,7 +468,11 @@ dconv_attention_tma_kernel(const __grid_constant__ CUtensorMap tm_q0, const __gr
             const int p0 = (sg - (which == 0 ? 0 : (which == 1 ? nsq : nsq + nsk))) * 16;
             const uint8_t* src = (which == 0 ? raw_q : (which == 1 ? raw_k : raw_v)) + p0 * ATT2_ROW_BYTES + hc4 * 8;
             uint8_t* dst = (which == 0 ? cv_q : (which == 1 ? cv_k : cv_v)) + p0 * ATT2_ROW_BYTES + (hc4 & 1) * 8;
-            conv_unit16(src, dst, hc4 >> 1, s_taps + which * DK * 4 + ((hc4 >> 1) % CPH) * 32 + (hc4 & 1) * 4);
+            const float* tp = s_taps + which * DK * 4 + ((hc4 >> 1) % CPH) * 32 + (hc4 & 1) * 4;
+            if (CONV_BF16)
+                conv_unit16_bf16(src, dst, hc4 >> 1, tp);
+            else
+                conv_unit16(src, dst, hc4 >> 1, tp);
         }
         __syncthreads();  // cv complete, raw free
         if (tid == 0 && item + n_stages * (int)gridDim.x < geo.n_items) issue_load(item + n_stages * gridDim.x, stage);
@@ -553,12 +581,19 @@ int make_rows_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t col
     return GD_OK;
 }
 
-template <int DK, int KB>
+// Conv arithmetic of the bf16 path: packed bf16x2 (default; in the chain -1.8 % tedexp / -5 % beat step time, final-pose
+// error vs the reference 4.45e-3 -> 4.63e-3 tedexp, 4.58e-3 -> 5.32e-3 beat, tolerance 2e-2) or fp32 FMA (GD_ATTN_CONV=f32).
+static bool conv_in_bf16() {
+    const char* e = getenv("GD_ATTN_CONV");
+    return !(e && e[0] == 'f');
+}
+
+template <int DK, int KB, bool CONV_BF16>
 static int launch_attention_tma(const AttnParams& p, int n_clips, cudaStream_t s) {
     constexpr int HG = 64 / DK;
     constexpr int MAXT = 256;  // 8 warps x 128 registers: two CTAs fill the register file of an SM exactly
     constexpr int MAXREG = KB <= 5 ? 96 : 128;  // short key ranges need fewer registers: 20 instead of 16 warps per SM
-    auto kern = dconv_attention_tma_kernel<DK, KB, MAXT, MAXREG>;
+    auto kern = dconv_attention_tma_kernel<DK, KB, MAXT, MAXREG, CONV_BF16>;
     const int Lq_pad = (p.Lq + 15) & ~15, Lk_pad = KB * 16;
     Attn2Geom geo{};
     geo.groups = p.heads / HG;
@@ -618,17 +653,18 @@ static int launch_attention_tma(const AttnParams& p, int n_clips, cudaStream_t s
 
 template <int DK>
 static int dispatch_kb_tma(const AttnParams& p, int n_clips, cudaStream_t s) {
+    const bool bf = conv_in_bf16();
     switch ((p.Lk + 15) / 16) {
-        case 1: return launch_attention_tma<DK, 1>(p, n_clips, s);
-        case 2: return launch_attention_tma<DK, 2>(p, n_clips, s);
-        case 3: return launch_attention_tma<DK, 3>(p, n_clips, s);
-        case 4: return launch_attention_tma<DK, 4>(p, n_clips, s);
-        case 5: return launch_attention_tma<DK, 5>(p, n_clips, s);
-        case 6: return launch_attention_tma<DK, 6>(p, n_clips, s);
-        case 7: return launch_attention_tma<DK, 7>(p, n_clips, s);
-        case 8: return launch_attention_tma<DK, 8>(p, n_clips, s);
-        case 9: return launch_attention_tma<DK, 9>(p, n_clips, s);
-        case 10: return launch_attention_tma<DK, 10>(p, n_clips, s);
+        case 1: return bf ? launch_attention_tma<DK, 1, true>(p, n_clips, s) : launch_attention_tma<DK, 1, false>(p, n_clips, s);
+        case 2: return bf ? launch_attention_tma<DK, 2, true>(p, n_clips, s) : launch_attention_tma<DK, 2, false>(p, n_clips, s);
+        case 3: return bf ? launch_attention_tma<DK, 3, true>(p, n_clips, s) : launch_attention_tma<DK, 3, false>(p, n_clips, s);
+        case 4: return bf ? launch_attention_tma<DK, 4, true>(p, n_clips, s) : launch_attention_tma<DK, 4, false>(p, n_clips, s);
+        case 5: return bf ? launch_attention_tma<DK, 5, true>(p, n_clips, s) : launch_attention_tma<DK, 5, false>(p, n_clips, s);
+        case 6: return bf ? launch_attention_tma<DK, 6, true>(p, n_clips, s) : launch_attention_tma<DK, 6, false>(p, n_clips, s);
+        case 7: return bf ? launch_attention_tma<DK, 7, true>(p, n_clips, s) : launch_attention_tma<DK, 7, false>(p, n_clips, s);
+        case 8: return bf ? launch_attention_tma<DK, 8, true>(p, n_clips, s) : launch_attention_tma<DK, 8, false>(p, n_clips, s);
+        case 9: return bf ? launch_attention_tma<DK, 9, true>(p, n_clips, s) : launch_attention_tma<DK, 9, false>(p, n_clips, s);
+        case 10: return bf ? launch_attention_tma<DK, 10, true>(p, n_clips, s) : launch_attention_tma<DK, 10, false>(p, n_clips, s);
     }
     return set_error(GD_ERR_INVALID, "gd_dconv_attention: need 0 < keys <= 160 (got %d)", p.Lk);
 }
