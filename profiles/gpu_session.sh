@@ -1,9 +1,6 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -x -q -m gpu -s 2>&1 | grep -E "final pose|passed|failed|rror" | tail -14
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout 900 python bench.py > gpurun_out/bench_v12_tedexp256.json 2> gpurun_out/bench_v12.err; tail -c 200 gpurun_out/bench_v12.err; python -c "
-import json; d=json.load(open('gpurun_out/bench_v12_tedexp256.json')); print(d['value'], d['ms_per_denoise_step'], d['e2e']['value'], d['roofline']['achieved'], d['clocks'], {k:v['ms_per_step'] for k,v in d['kernel_breakdown'].items()})"
-timeout 600 python bench.py --workload beat-ours > gpurun_out/bench_v12_beat1024.json 2>/dev/null; python -c "
-import json; d=json.load(open('gpurun_out/bench_v12_beat1024.json')); print(d['value'], d['ms_per_denoise_step'], d['e2e']['value'], d['roofline']['achieved'], d['clocks'], {k:v['ms_per_step'] for k,v in d['kernel_breakdown'].items()})"
-timeout 600 python bench.py --workload beat-ours-4x --no-cpu-baseline > gpurun_out/bench_v12_beat4x64.json 2>/dev/null; python -c "
-import json; d=json.load(open('gpurun_out/bench_v12_beat4x64.json')); print(d['value'], d['ms_per_denoise_step'])"
+timeout 300 python -m pytest tests/test_kernels_gpu.py -x -q -k "layernorm or ddpm" 2>&1 | tail -3
+timeout 300 python profiles/kernel_bench.py layernorm 2>&1 | tail -4
+timeout 300 python profiles/kernel_bench.py ddpm 2>&1 | tail -4
+for w in tedexp-ours beat-ours; do timeout 300 python bench.py --workload $w --steps 1 --warmup 1 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('$w', round(d['value'],1), round(d['ms_per_denoise_step'],3), {k:v['ms_per_step'] for k,v in d['kernel_breakdown'].items()}, d['clocks']['sm_mhz'])"; done

@@ -11,7 +11,7 @@ namespace gd {
 // One warp per row, the whole row lives in registers (D/32 floats per lane): one HBM read,
 // one bf16 write, two shuffle reductions (mean, then centred second moment like ATen's
 // two-pass/Welford result — not E[x^2]-E[x]^2, which loses bits when |mean| >> std).
-template <int D>
+template <int D, int R>
 __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __restrict__ x, int ldx,
                                                              const float* __restrict__ gamma,
                                                              const float* __restrict__ beta,
@@ -19,36 +19,45 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
                                                              float eps) {
     pdl_launch_dependents();
     pdl_wait();
-    constexpr int V = D / 128;  // float4 chunks per lane
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= M) return;
+    constexpr int V = D / 128;  // float4 chunks per lane and row
+    // a warp owns R consecutive rows and issues all their loads before the first reduction (more bytes in flight per warp)
+    const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+    if (row0 >= M) return;
     const int lane = threadIdx.x & 31;
-    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ldx);
-    float4 v[V];
-    float s = 0.f;
+    float4 v[R][V];
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-        v[i] = xr[i * 32 + lane];
-        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
-    const float mean = warp_sum(s) * (1.0f / D);
-    float q = 0.f;
+    for (int r = 0; r < R; ++r) {
+        const int row = min(row0 + r, M - 1);
+        const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ldx);
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-        q += (a * a + b * b) + (c * c + d * d);
+        for (int i = 0; i < V; ++i) v[r][i] = xr[i * 32 + lane];
     }
-    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
     const float4* g4 = reinterpret_cast<const float4*>(gamma);
     const float4* b4 = reinterpret_cast<const float4*>(beta);
-    uint2* orow = reinterpret_cast<uint2*>(out + (size_t)row * ldo);
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-        const float4 g = __ldg(g4 + i * 32 + lane), b = __ldg(b4 + i * 32 + lane);
-        uint2 w;
-        w.x = pack_bf16x2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
-        w.y = pack_bf16x2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
-        orow[i * 32 + lane] = w;
+    for (int r = 0; r < R; ++r) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) s += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+        const float mean = warp_sum(s) * (1.0f / D);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const float a = v[r][i].x - mean, b = v[r][i].y - mean, c = v[r][i].z - mean, d = v[r][i].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+        const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+        if (row0 + r < M) {
+            uint2* orow = reinterpret_cast<uint2*>(out + (size_t)(row0 + r) * ldo);
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                const float4 g = __ldg(g4 + i * 32 + lane), b = __ldg(b4 + i * 32 + lane);
+                uint2 w;
+                w.x = pack_bf16x2((v[r][i].x - mean) * rstd * g.x + b.x, (v[r][i].y - mean) * rstd * g.y + b.y);
+                w.y = pack_bf16x2((v[r][i].z - mean) * rstd * g.z + b.z, (v[r][i].w - mean) * rstd * g.w + b.w);
+                orow[i * 32 + lane] = w;
+            }
+        }
     }
 }
 
@@ -194,16 +203,17 @@ extern "C" int gd_layernorm(const float* x, int32_t ldx, const float* gamma, con
     if (M <= 0) return set_error(GD_ERR_INVALID, "gd_layernorm: M <= 0");
     if (ldx % 4 || ldo % 4 || ldx < D || ldo < D) return set_error(GD_ERR_INVALID, "gd_layernorm: bad row stride");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    const int wpb = 8, grid = (M + wpb - 1) / wpb;
+    constexpr int R = 2;  // rows per warp
+    const int wpb = 8, grid = (M + wpb * R - 1) / (wpb * R);
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
     if (D == 256) {
-        GD_CUDA_CHECK(launch_k(layernorm_rows_kernel<256>, grid, wpb * 32, 0, s, 1, x, ldx, gamma, beta, o, ldo, M, eps));
+        GD_CUDA_CHECK(launch_k(layernorm_rows_kernel<256, R>, grid, wpb * 32, 0, s, 1, x, ldx, gamma, beta, o, ldo, M, eps));
     } else if (D == 512) {
-        GD_CUDA_CHECK(launch_k(layernorm_rows_kernel<512>, grid, wpb * 32, 0, s, 1, x, ldx, gamma, beta, o, ldo, M, eps));
+        GD_CUDA_CHECK(launch_k(layernorm_rows_kernel<512, R>, grid, wpb * 32, 0, s, 1, x, ldx, gamma, beta, o, ldo, M, eps));
     } else if (D == 128) {
-        GD_CUDA_CHECK(launch_k(layernorm_rows_kernel<128>, grid, wpb * 32, 0, s, 1, x, ldx, gamma, beta, o, ldo, M, eps));
+        GD_CUDA_CHECK(launch_k(layernorm_rows_kernel<128, R>, grid, wpb * 32, 0, s, 1, x, ldx, gamma, beta, o, ldo, M, eps));
     } else if (D == 1024) {
-        GD_CUDA_CHECK(launch_k(layernorm_rows_kernel<1024>, grid, wpb * 32, 0, s, 1, x, ldx, gamma, beta, o, ldo, M, eps));
+        GD_CUDA_CHECK(launch_k(layernorm_rows_kernel<1024, R>, grid, wpb * 32, 0, s, 1, x, ldx, gamma, beta, o, ldo, M, eps));
     } else {
         return set_error(GD_ERR_INVALID, "gd_layernorm: D=%d unsupported (128/256/512/1024)", D);
     }

@@ -675,5 +675,6 @@ extern "C" int gd_linear_ddpm(const gd_linear_desc* d, const gd_ddpm_desc* u, vo
     p.M = d->M, p.N = d->N, p.K = d->K;
     p.bias = d->bias;
     p.ddpm = *u;
-    return launch_gemm<128, MODE_DDPM>(p, d->A, d->lda, d->W, d->ldw, reinterpret_cast<cudaStream_t>(stream));
+    // 128 x 64 tiles: twice as many CTAs share the (epilogue-bound) update - the whole pose matrix is only 68..320 m-tiles
+    return launch_gemm<64, MODE_DDPM>(p, d->A, d->lda, d->W, d->ldw, reinterpret_cast<cudaStream_t>(stream));
 }
