@@ -159,7 +159,7 @@ def run_reference(args):
             "config": {"workload": f"{args.workload} full 1000-step DDPM chain", "clips_per_sample": clips},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": th.get_num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------- B200 arm
@@ -364,12 +364,23 @@ def run_b200(args):
             "gpu_launches": len(chain.plan) * n_steps * args.steps, "kernels_per_denoise_step": len(chain.plan),
             "lib_launch_counter": int(lib.gd_launch_count()),
             "roofline": roofline, "kernel_breakdown": breakdown, "cpu_baseline": cpu}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def emit(line):
+    """The ONE JSON line of the contract, on the real stdout."""
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 if __name__ == "__main__":
+    # Libraries print banners on fd 1 (NCCL: "NCCL version ..." when NCCL_DEBUG is set in the environment); keep stdout for
+    # the JSON line alone by pointing fd 1 at stderr for everything else.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         run_reference(a)

@@ -1,6 +1,5 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_kernels_gpu.py -x -q -k "layernorm or ddpm" 2>&1 | tail -3
-timeout 300 python profiles/kernel_bench.py layernorm 2>&1 | tail -4
-timeout 300 python profiles/kernel_bench.py ddpm 2>&1 | tail -4
-for w in tedexp-ours beat-ours; do timeout 300 python bench.py --workload $w --steps 1 --warmup 1 --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('$w', round(d['value'],1), round(d['ms_per_denoise_step'],3), {k:v['ms_per_step'] for k,v in d['kernel_breakdown'].items()}, d['clocks']['sm_mhz'])"; done
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_v13_tedexp256_2gpu.json 2> gpurun_out/bench_2gpu.err; tail -c 300 gpurun_out/bench_2gpu.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_v13_tedexp256_2gpu.json')); print(d['n_gpus'], d['value'], d['ms_per_denoise_step'], d['e2e']['value'], d['clocks'])"
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --impl reference --steps 2 --warmup 1 2>/dev/null | cut -c1-400
+timeout 300 python -m pytest tests/test_chain_gpu.py -x -q 2>&1 | tail -2
