@@ -117,6 +117,25 @@ def test_fused_layernorm_plan_matches_two_kernel_plan(name):
     assert err < 5e-3, f"{name}: fused vs two-kernel plan rel-L2 {err:.3e}"
 
 
+@pytest.mark.parametrize("name", ["beat", "tedexp"])
+def test_single_clip_chain_vs_oracle(name):
+    """BASELINE config 1 shape: one clip (34 / 40 token rows, far less than one 128-row tile) through the public API."""
+    from oracle import ddpm_oracle as orc
+    from gesture_b200.generator import Generator
+    model, diffusion, C, T, L, params = build(name, "boost", respacing="ddim10")
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    tabs = oracle_tables(params.Diffusion)
+    wav = synthetic_wav(1, L, seed=23)
+    x_T, tape = noise_tape((1, C, T), 10, seed=10)
+    ref = orc.sample_chain(sd, params.type, params.Decoder.heads, tabs, x_T, wav, tape, alg="ddpm")
+    model.to("cuda")
+    out = Generator(model, diffusion).generate_sample((1, C, T), wav, noise=x_T, sample_alg="ddpm", device="cuda", progress=False,
+                                                      noise_tape=tape)
+    assert out.shape == (1, T, C)
+    err = rel_l2(out.transpose(1, 2), ref)
+    assert err < 2e-2, f"{name}: single-clip final pose rel-L2 {err:.3e}"
+
+
 def test_long_form_beat_4x_length():
     """BASELINE config 5: the beat model at 4x the config's sequence length (T=160, wav 128 000 -> 127 memory tokens):
     160-query / 127- and 160-key attention tiles, same weights."""
