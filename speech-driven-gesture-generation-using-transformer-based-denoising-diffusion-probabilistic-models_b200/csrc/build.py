@@ -1,13 +1,15 @@
-"""Builds libgd_b200.so (all CUDA kernels + the C-ABI) for sm_100a with nvcc; no GPU needed."""
+"""Builds libgd_b200.so (all CUDA kernels + the C-ABI) for sm_100a with nvcc; no GPU needed.
+Translation units are compiled in parallel (one nvcc -c per .cu) and linked into the shared library."""
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["api.cu", "gemm_tcgen05.cu", "gemm_resid_ln.cu", "elementwise.cu", "attention.cu", "attention_tc.cu"]
 OUT = os.path.join(os.path.dirname(HERE), "libgd_b200.so")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--compiler-options", "-fPIC",
-         "-shared", "-lcudart"]
+OBJ_DIR = os.path.join(HERE, "_obj")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--compiler-options", "-fPIC"]
 
 
 def needs_build():
@@ -23,8 +25,17 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(HERE, s) for s in SOURCES]
-    subprocess.run(cmd, check=True, cwd=HERE)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    extra = ["-Xptxas", "-v"] if verbose else []
+
+    def compile_one(src):
+        obj = os.path.join(OBJ_DIR, src[:-3] + ".o")
+        subprocess.run([nvcc] + FLAGS + extra + ["-c", os.path.join(HERE, src), "-o", obj], check=True, cwd=HERE)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + objs + ["-lcudart"], check=True, cwd=HERE)
     return OUT
 
 
