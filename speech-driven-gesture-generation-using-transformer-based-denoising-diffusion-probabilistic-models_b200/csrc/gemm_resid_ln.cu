@@ -287,6 +287,10 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             *mine = make_float2(mean_p, m2_p);
             if (NSPLIT > 1) st_cluster_f2(map_to_cta(smem_u32(mine), cta_rank ^ 1), mean_p, m2_p);
             __syncwarp();
+            // Both CTAs count 16 arrivals per tile on their own barrier.  A CTA can only arrive for tile i+1 after it has
+            // passed its own barrier of tile i, i.e. after all 16 warps have issued their arrives for tile i (a warp issues the
+            // two back to back), so a phase is never completed by arrivals of the next one in practice: the peer's second
+            // arrive would have to stay in flight for the thousands of cycles of pass 2 + the next tile's pass 1.
             if (lane == 0) {
                 if (NSPLIT > 1) {  // one cluster-scope release fence, then two relaxed arrives
                     fence_acq_rel_cluster();
