@@ -116,3 +116,20 @@ def test_inpaint_blend_matches_reference_formula():
     assert th.equal(blend(x0), ref)
     hard = InpaintBlend(seed, masks, None, None, T)  # trans_factor None -> seed frames copied
     assert th.equal(hard(x0).transpose(1, 2)[:, :seed_len], seed[:, :seed_len])
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """Driver contract: `bench.py --impl reference` runs on the host alone and prints exactly one JSON line on stdout
+    (library banners must not leak into it), with the keys of the reference arm."""
+    import json
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([_sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
