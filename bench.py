@@ -48,7 +48,8 @@ def parse():
                     help="beat-ours-4x = BASELINE config 5: the beat model at 4x its window (160 frames, 8 s of speech)")
     ap.add_argument("--clips", type=int, default=None, help="clips per GPU (default 256 tedexp / 1024 beat / 64 beat-4x)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32act"])
-    ap.add_argument("--graph-steps", type=int, default=10, help="denoise steps captured per CUDA graph")
+    ap.add_argument("--graph-steps", type=int, default=0,
+                    help="denoise steps captured per CUDA graph (0 = the whole chain as one graph, the default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -354,7 +355,7 @@ def run_b200(args):
             "dtype": "bf16" if args.precision == "bf16" else "bf16 operands / fp32 activations", "data": "synthetic",
             "config": {"workload": f"{args.workload} full {n_steps}-step DDPM chain, {clips} clips/GPU x {T} frames, random-init weights "
                                    "(seed 0), synthetic speech, CUDA-graphed chain", "clips_per_gpu": clips, "frames": T,
-                       "d_pose": C, "denoise_steps": n_steps, "graph_steps": args.graph_steps,
+                       "d_pose": C, "denoise_steps": n_steps, "graph_steps": args.graph_steps or n_steps,
                        "l2_policy": "inputs_larger_than_L2 (per-step activations + 1000-step noise tape >> 126 MB)",
                        "parallelism": f"clip-sharded x{world}, all_gather of poses"},
             "ms_per_denoise_step": ms_replay / n_steps, "chain_replay_ms": ms_replay,

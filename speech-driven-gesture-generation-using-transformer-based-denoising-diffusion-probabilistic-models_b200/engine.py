@@ -10,7 +10,8 @@ Data layout in HBM (per engine, N clips):
   hid      [rows, 4d] bf16     FFN hidden after squared ReLU
   tape     (n_steps, N, C, T)  pre-generated Gaussian noise indexed by loop index i
 The step index lives in a device int; every kernel that depends on it reads it there, so ONE captured
-step graph serves all steps and `graph_steps` consecutive steps can be captured into a single graph.
+step graph serves all steps; by default the whole T-step chain is captured as one CUDA graph (`graph_steps` = 0), a
+positive `graph_steps` captures that many consecutive steps per graph instead.
 """
 import ctypes as C
 import math
@@ -188,7 +189,9 @@ class SamplingChain:
         self.device = device
         self.precision = precision
         self.f32act = precision == "fp32act"
-        self.graph_steps, self.use_graph = graph_steps, use_graph
+        # denoise steps per captured CUDA graph; 0 = the whole chain as ONE graph (the default: 1000 steps = ~190 k kernel nodes,
+        # captured once per (model, shape) and replayed for every chain)
+        self.graph_steps, self.use_graph = (graph_steps if graph_steps and graph_steps > 0 else diffusion.num_timesteps), use_graph
         self.L = _Launcher()
         self.W = model.packed_weights(diffusion, device)
         if self.C != self.W.C:
@@ -591,7 +594,7 @@ def chain_for(model, diffusion, shape, alg, device, **kw):
     device = th.device(device)
     if device.type == "cuda" and device.index is None:
         device = th.device("cuda", th.cuda.current_device())
-    opts = dict(precision=getattr(model, "precision", "bf16"), graph_steps=getattr(model, "graph_steps", 1),
+    opts = dict(precision=getattr(model, "precision", "bf16"), graph_steps=getattr(model, "graph_steps", 0),
                 use_graph=getattr(model, "use_graph", True), fuse_ln=getattr(model, "fuse_layernorm", False))
     opts.update(kw)
     key = (id(model), id(diffusion), shape, alg, str(device), model.weights_version, tuple(sorted(opts.items())))

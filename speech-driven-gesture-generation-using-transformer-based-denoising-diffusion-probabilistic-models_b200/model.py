@@ -38,7 +38,7 @@ class Speech2GestureDenoiser(nn.Module):
                 if isinstance(m, nn.Linear):
                     m.weight.data.zero_()
                     m.bias.data.zero_()
-        self.precision, self.graph_steps, self.use_graph = "bf16", 1, True
+        self.precision, self.graph_steps, self.use_graph = "bf16", 0, True  # graph_steps 0: whole chain in one CUDA graph
         self.weights_version = 0
         self._packed = None
         self._diffusion = None
