@@ -30,6 +30,7 @@ constexpr int MODE_DIRECT = 0;    // per-row stores straight from registers (any
 constexpr int MODE_DDPM = 1;      // final projection + DDPM update
 constexpr int MODE_TMA_BF16 = 2;  // bf16 output through TMA stores
 constexpr int MODE_TMA_F32 = 3;   // fp32 output through TMA stores, or TMA reduce-add when accumulating in place
+constexpr int MODE_CONV = 4;      // implicit-GEMM convolution over pixel rows (gd_conv_taps_bf16): shifted A tiles per tap
 
 struct GemmParams {
     int M, N, K;
@@ -45,6 +46,15 @@ struct GemmParams {
     int ldo_bf16;
     int reduce_add;  // MODE_TMA_F32: 1 = out += result (in-place residual), 0 = out = result
     gd_ddpm_desc ddpm;
+    // MODE_CONV: k-block kb reads A rows m0 + tap_shift[kb / kb_per_tap], columns (kb % kb_per_tap) * 64
+    int kb_per_tap;
+    int tap_shift[GD_CONV_MAX_TAPS];
+    const float* scale;   // per output channel, applied after bias (+ReLU): folded BatchNorm
+    const float* shift;
+    int relu;
+    int grid_h, grid_w;   // pixel grid of one image (rows per image = grid_h * grid_w)
+    int y0, y1, x0, x1, stride;
+    int out_img_stride, out_y_stride, out_x_stride, out_offset;  // output row of a kept pixel
 };
 
 template <int BN, int CL>
@@ -132,6 +142,42 @@ __device__ __forceinline__ void epilogue_direct_chunk(const GemmParams& p, int r
             w.w = pack_bf16x2(r[8 * j + 6], r[8 * j + 7]);
             o4[j] = w;
         }
+    }
+}
+
+// MODE_CONV: v = (relu?)(acc + bias) * scale + shift -> bf16, 32 channels of one kept pixel (64 contiguous bytes)
+__device__ __forceinline__ void epilogue_conv_chunk(const GemmParams& p, size_t out_row, int col0, const uint32_t (&v)[32]) {
+    float r[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        r[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
+        r[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+        r[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+        r[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+    }
+    if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = fmaxf(r[j], 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + col0) + j);
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + col0) + j);
+        r[4 * j + 0] = fmaf(r[4 * j + 0], sc.x, sh.x);
+        r[4 * j + 1] = fmaf(r[4 * j + 1], sc.y, sh.y);
+        r[4 * j + 2] = fmaf(r[4 * j + 2], sc.z, sh.z);
+        r[4 * j + 3] = fmaf(r[4 * j + 3], sc.w, sh.w);
+    }
+    uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + out_row * p.ldo_bf16 + col0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint4 w;
+        w.x = pack_bf16x2(r[8 * j + 0], r[8 * j + 1]);
+        w.y = pack_bf16x2(r[8 * j + 2], r[8 * j + 3]);
+        w.z = pack_bf16x2(r[8 * j + 4], r[8 * j + 5]);
+        w.w = pack_bf16x2(r[8 * j + 6], r[8 * j + 7]);
+        o4[j] = w;
     }
 }
 
@@ -280,7 +326,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (CL == 1) {
                         mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                        tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K, m0);
+                        int a_col = kb * BLOCK_K, a_row = m0;
+                        if (MODE == MODE_CONV) {  // tap-shifted pixel rows; rows outside [0, M) are zero-filled by TMA
+                            const int tap = kb / p.kb_per_tap;
+                            a_col = (kb - tap * p.kb_per_tap) * BLOCK_K;
+                            a_row = m0 + p.tap_shift[tap];
+                        }
+                        tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_a, &full_bar[stage], a_col, a_row);
                         tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmap_b, &full_bar[stage], kb * BLOCK_K, n0);
                     } else {
                         // both CTAs fill their own slot; all bytes are counted on the leader's barrier
@@ -382,6 +434,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         mbar_arrive_cluster(map_to_cta(smem_u32(&acc_empty_bar[acc]), 0));
                 }
             };
+            bool conv_keep = false;
+            size_t conv_out_row = 0;
+            if (MODE == MODE_CONV) {  // pixel row -> (image, y, x); only pixels inside the window (and on the stride) are stored
+                const int gsz = p.grid_h * p.grid_w;
+                const int img = row / gsz;
+                const int rem = row - img * gsz;
+                const int y = rem / p.grid_w, x = rem - y * p.grid_w;
+                int dy = y - p.y0, dx = x - p.x0;
+                conv_keep = row < p.M && y >= p.y0 && y <= p.y1 && x >= p.x0 && x <= p.x1;
+                if (p.stride == 2) {
+                    conv_keep = conv_keep && ((dy | dx) & 1) == 0;
+                    dy >>= 1, dx >>= 1;
+                }
+                conv_out_row = (size_t)img * p.out_img_stride + (size_t)(dy * p.out_y_stride + dx * p.out_x_stride + p.out_offset);
+            }
             if constexpr (MODE == MODE_TMA_BF16 && WCOLS >= 64) {
                 // bf16 output, 64 columns (one 128-B swizzled row per lane) per TMA store: half as many fences / stores /
                 // staging hand-offs as 32-column chunks, and the next TMEM load is in flight while this one is stored
@@ -494,6 +561,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             tma_store_2d(&tmap_out, stg, col0, row0);
                         bulk_commit_group();
                     }
+                } else if (MODE == MODE_CONV) {
+                    tmem_ld_wait();
+                    if (c == WCOLS / 32 - 1) release_accumulator();
+                    if (conv_keep) epilogue_conv_chunk(p, conv_out_row, col0, v);
                 } else {
                     tmem_ld_wait();
                     if (row < p.M) {
@@ -592,10 +663,34 @@ template <int BN, int MODE>
 static int launch_gemm(const GemmParams& p, const void* A, int lda, const void* W, int ldw, cudaStream_t stream) {
     const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
     const int policy = cta_pair_policy();
-    if (BN >= 128 && MODE != MODE_DDPM && MODE != MODE_DIRECT && policy > 0 && (p.K >= 1024 || policy == 2) &&
+    if (BN >= 128 && MODE != MODE_DDPM && MODE != MODE_DIRECT && MODE != MODE_CONV && policy > 0 && (p.K >= 1024 || policy == 2) &&
         ((m_tiles + 1) / 2) * (p.N / BN) >= sm_count() / 2)
         return launch_gemm_cl<BN, MODE, 2>(p, A, lda, W, ldw, stream);
     return launch_gemm_cl<BN, MODE, 1>(p, A, lda, W, ldw, stream);
+}
+
+// MODE_CONV: the A operand is the pixel-row tensor [rows, c_in]; every tap reads the same columns at shifted rows, and
+// W is [c_out, n_taps * c_in] with the taps along K.
+template <int BN>
+static int launch_conv(const GemmParams& p, const void* A, int c_in, const void* W, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN, 1>;
+    CUtensorMap ta, tb;
+    int rc = make_tmap_2d_bf16(&ta, A, p.M, c_in, c_in, BLOCK_M);
+    if (rc) return rc;
+    rc = make_tmap_2d_bf16(&tb, W, p.N, p.K, p.K, BN);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GD_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, MODE_CONV, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int work = ((p.M + BLOCK_M - 1) / BLOCK_M) * (p.N / BN);
+    const int grid = work < sm_count() ? work : sm_count();
+    GD_CUDA_CHECK(launch_k(gemm_bf16_tn_kernel<BN, MODE_CONV, 1>, grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream, 1, ta, tb, ta, p));
+    count_launch();
+    GD_CUDA_CHECK(cudaGetLastError());
+    return GD_OK;
 }
 
 static int validate_linear(const gd_linear_desc* d) {
@@ -677,4 +772,40 @@ extern "C" int gd_linear_ddpm(const gd_linear_desc* d, const gd_ddpm_desc* u, vo
     p.ddpm = *u;
     // 128 x 64 tiles: twice as many CTAs share the (epilogue-bound) update - the whole pose matrix is only 68..320 m-tiles
     return launch_gemm<64, MODE_DDPM>(p, d->A, d->lda, d->W, d->ldw, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gd_conv_taps_bf16(const gd_conv_desc* d, void* stream) {
+    if (!d || !d->in || !d->W || !d->out || !d->scale || !d->shift)
+        return set_error(GD_ERR_INVALID, "gd_conv_taps_bf16: null descriptor/operand");
+    if (d->n_images <= 0 || d->grid_h <= 0 || d->grid_w <= 0) return set_error(GD_ERR_INVALID, "gd_conv_taps_bf16: empty grid");
+    if (d->c_in <= 0 || d->c_in % BLOCK_K || d->c_out <= 0 || d->c_out % 64)
+        return set_error(GD_ERR_INVALID, "gd_conv_taps_bf16: c_in=%d / c_out=%d must be multiples of 64", d->c_in, d->c_out);
+    if (d->n_taps < 1 || d->n_taps > GD_CONV_MAX_TAPS) return set_error(GD_ERR_INVALID, "gd_conv_taps_bf16: n_taps out of range");
+    if (d->stride != 1 && d->stride != 2) return set_error(GD_ERR_INVALID, "gd_conv_taps_bf16: stride must be 1 or 2");
+    if (d->y0 < 0 || d->y1 >= d->grid_h || d->x0 < 0 || d->x1 >= d->grid_w || d->y0 > d->y1 || d->x0 > d->x1)
+        return set_error(GD_ERR_INVALID, "gd_conv_taps_bf16: output window outside the grid");
+    if (d->out_ld % 8 || d->out_ld < d->c_out) return set_error(GD_ERR_INVALID, "gd_conv_taps_bf16: out_ld must be >= c_out and a multiple of 8");
+    const int64_t rows = (int64_t)d->n_images * d->grid_h * d->grid_w;
+    if (rows >= ((int64_t)1 << 31) - 65536) return set_error(GD_ERR_INVALID, "gd_conv_taps_bf16: too many pixel rows");
+    if ((reinterpret_cast<uintptr_t>(d->in) | reinterpret_cast<uintptr_t>(d->W) | reinterpret_cast<uintptr_t>(d->out)) & 15)
+        return set_error(GD_ERR_INVALID, "gd_conv_taps_bf16: in/W/out must be 16-byte aligned");
+    int rc = check_device();
+    if (rc) return rc;
+    GemmParams p{};
+    p.M = (int)rows, p.N = d->c_out, p.K = d->n_taps * d->c_in;
+    p.bias = d->bias, p.scale = d->scale, p.shift = d->shift, p.relu = d->relu;
+    p.kb_per_tap = d->c_in / BLOCK_K;
+    for (int t = 0; t < d->n_taps; ++t) p.tap_shift[t] = d->tap_shift[t];
+    p.grid_h = d->grid_h, p.grid_w = d->grid_w;
+    p.y0 = d->y0, p.y1 = d->y1, p.x0 = d->x0, p.x1 = d->x1, p.stride = d->stride;
+    p.out_img_stride = d->out_img_stride, p.out_y_stride = d->out_y_stride, p.out_x_stride = d->out_x_stride;
+    p.out_offset = d->out_offset;
+    p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(d->out), p.ldo_bf16 = d->out_ld;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+    const int bn = (d->c_out % 256 == 0 && m_tiles * (d->c_out / 256) >= sm_count()) ? 256
+                   : (d->c_out % 128 == 0 && m_tiles * (d->c_out / 128) >= sm_count()) ? 128 : 64;
+    if (bn == 256) return launch_conv<256>(p, d->in, d->c_in, d->W, s);
+    if (bn == 128) return launch_conv<128>(p, d->in, d->c_in, d->W, s);
+    return launch_conv<64>(p, d->in, d->c_in, d->W, s);
 }

@@ -1,0 +1,248 @@
+// Row kernels of the once-per-clip speech encoder (ResNetSE-34 trunk of HA2GSpeechEncoder) around the tensor-core
+// convolutions (gemm_tcgen05.cu, MODE_CONV): the 1-channel stem, the squeeze-excite gate, the block tail and the pixel
+// shuffles of the pyramid heads.  Feature maps are channel-last bf16 pixel rows on zero-bordered grids (gd_b200.h);
+// every kernel here is HBM/L2-bound, 16-byte vectorised along the channels, and none of them writes a border pixel.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace gd {
+
+static inline int grid_for(size_t total, int block) { return (int)((total + block - 1) / block); }
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4& q, float (&f)[8]) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ stem
+// conv1 (1 -> c_real, 3x3, zero padding, bias) + ReLU + folded BatchNorm.  One thread = one pixel x 8 channels.
+__global__ void __launch_bounds__(256) speech_stem_kernel(const float* __restrict__ mel, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
+                                                          int n_images, int H, int W, int c_real, int c_pad) {
+    extern __shared__ float s_par[];  // [c_real*9 | c_real | c_real | c_real]
+    pdl_launch_dependents();
+    pdl_wait();
+    float* s_w = s_par;
+    float* s_b = s_w + c_real * 9;
+    float* s_sc = s_b + c_real;
+    float* s_sh = s_sc + c_real;
+    for (int i = threadIdx.x; i < c_real * 9; i += blockDim.x) s_w[i] = w[i];
+    for (int i = threadIdx.x; i < c_real; i += blockDim.x) s_b[i] = bias[i], s_sc[i] = scale[i], s_sh[i] = shift[i];
+    __syncthreads();
+    const int groups = c_pad >> 3;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t pix = idx / groups;
+    const int g = (int)(idx - pix * groups);
+    if (pix >= (size_t)n_images * H * W) return;
+    const int img = (int)(pix / ((size_t)H * W));
+    const int rem = (int)(pix - (size_t)img * H * W);
+    const int y = rem / W, x = rem - y * W;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (g * 8 < c_real) {
+        float m[9];
+        const float* base = mel + (size_t)img * H * W;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int yy = y + ky - 1, xx = x + kx - 1;
+                m[ky * 3 + kx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(base + yy * W + xx) : 0.f;
+            }
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = g * 8 + j;
+            float acc = 0.f;
+            if (c < c_real) {
+#pragma unroll
+                for (int t = 0; t < 9; ++t) acc = fmaf(s_w[c * 9 + t], m[t], acc);
+                acc = fmaxf(acc + s_b[c], 0.f) * s_sc[c] + s_sh[c];
+            }
+            r[j] = acc;
+        }
+        o = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
+    }
+    const size_t orow = (size_t)img * (H + 2) * (W + 2) + (size_t)(y + 1) * (W + 2) + (x + 1);
+    reinterpret_cast<uint4*>(out + orow * c_pad)[g] = o;
+}
+
+// ------------------------------------------------------------------------------------------ squeeze-excite gate
+// One CTA per image: channel sums over every pixel row of the grid (the border is zero) in a fixed order, then the two
+// tiny Linear layers.  c <= 256.
+__global__ void __launch_bounds__(256) se_gate_kernel(const __nv_bfloat16* __restrict__ y, int grid_px, int interior_px, int c,
+                                                      int c_real, int c_hidden, const float* __restrict__ w1,
+                                                      const float* __restrict__ b1, const float* __restrict__ w2,
+                                                      const float* __restrict__ b2, float* __restrict__ gate) {
+    __shared__ float s_part[256 * 8];
+    __shared__ float s_mean[256];
+    __shared__ float s_hid[32];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int img = blockIdx.x;
+    const int groups = c >> 3;            // 8-channel groups per pixel row
+    const int lanes = 256 / groups;       // pixel rows read concurrently
+    const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const uint4* base = reinterpret_cast<const uint4*>(y + (size_t)img * grid_px * c);
+    if (pl < lanes) {
+        for (int p = pl; p < grid_px; p += lanes) {
+            float f[8];
+            unpack_bf16x8(__ldg(base + (size_t)p * groups + g), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_part[threadIdx.x * 8 + j] = acc[j];
+    __syncthreads();
+    if (threadIdx.x < c) {
+        const int ch = threadIdx.x, cg = ch >> 3, cj = ch & 7;
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += s_part[(l * groups + cg) * 8 + cj];
+        s_mean[ch] = s / (float)interior_px;
+    }
+    __syncthreads();
+    if (threadIdx.x < c_hidden) {
+        float h = b1[threadIdx.x];
+        for (int i = 0; i < c_real; ++i) h = fmaf(w1[threadIdx.x * c_real + i], s_mean[i], h);
+        s_hid[threadIdx.x] = fmaxf(h, 0.f);
+    }
+    __syncthreads();
+    if (threadIdx.x < c) {
+        float gv = 0.f;
+        if (threadIdx.x < c_real) {
+            float a = b2[threadIdx.x];
+            for (int j = 0; j < c_hidden; ++j) a = fmaf(w2[threadIdx.x * c_hidden + j], s_hid[j], a);
+            gv = 1.0f / (1.0f + __expf(-a));
+        }
+        gate[(size_t)img * c + threadIdx.x] = gv;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ block tail
+// out = relu(gate * y + residual) on the interior pixels.  One thread = one pixel x 8 channels.
+__global__ void __launch_bounds__(256) se_residual_relu_kernel(const __nv_bfloat16* __restrict__ y,
+                                                               const __nv_bfloat16* __restrict__ res,
+                                                               const float* __restrict__ gate, __nv_bfloat16* __restrict__ out,
+                                                               int n_images, int grid_h, int grid_w, int c) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int groups = c >> 3;
+    const int H = grid_h - 2, W = grid_w - 2;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t pix = idx / groups;
+    const int g = (int)(idx - pix * groups);
+    if (pix >= (size_t)n_images * H * W) return;
+    const int img = (int)(pix / ((size_t)H * W));
+    const int rem = (int)(pix - (size_t)img * H * W);
+    const int py = rem / W, px = rem - py * W;
+    const size_t row = (size_t)img * grid_h * grid_w + (size_t)(py + 1) * grid_w + (px + 1);
+    float a[8], r[8];
+    unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(y + row * c) + g), a);
+    unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(res + row * c) + g), r);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + (size_t)img * c) + 2 * g);
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + (size_t)img * c) + 2 * g + 1);
+    const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaxf(fmaf(gv[j], a[j], r[j]), 0.f);
+    reinterpret_cast<uint4*>(out + row * c)[g] =
+        make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+}
+
+// ------------------------------------------------------------------------------------------ pixel shuffle
+// out[img, y*r+i, x*r+j, ch] = in[img, y+1, x+1, ch*r*r + i*r + j]; ch >= c_in/r^2 written as 0.
+__global__ void __launch_bounds__(256) pixel_shuffle_rows_kernel(const __nv_bfloat16* __restrict__ in,
+                                                                 __nv_bfloat16* __restrict__ out, int n_images, int H, int W,
+                                                                 int c_in, int r, int c_out_pad) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int groups = c_out_pad >> 3;
+    const int Ho = H * r, Wo = W * r, c_real = c_in / (r * r);
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t pix = idx / groups;
+    const int g = (int)(idx - pix * groups);
+    if (pix >= (size_t)n_images * Ho * Wo) return;
+    const int img = (int)(pix / ((size_t)Ho * Wo));
+    const int rem = (int)(pix - (size_t)img * Ho * Wo);
+    const int oy = rem / Wo, ox = rem - oy * Wo;
+    const int y = oy / r, i = oy - y * r, x = ox / r, j = ox - x * r;
+    const unsigned short* src = reinterpret_cast<const unsigned short*>(in) +
+                                ((size_t)img * (H + 2) * (W + 2) + (size_t)(y + 1) * (W + 2) + (x + 1)) * c_in + i * r + j;
+    unsigned short v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int ch = g * 8 + k;
+        v[k] = ch < c_real ? __ldg(src + ch * r * r) : (unsigned short)0;
+    }
+    uint4 o;
+    o.x = v[0] | ((uint32_t)v[1] << 16), o.y = v[2] | ((uint32_t)v[3] << 16);
+    o.z = v[4] | ((uint32_t)v[5] << 16), o.w = v[6] | ((uint32_t)v[7] << 16);
+    reinterpret_cast<uint4*>(out + pix * c_out_pad)[g] = o;
+}
+
+}  // namespace gd
+
+using namespace gd;
+
+extern "C" int gd_speech_stem(const float* mel, const float* w, const float* bias, const float* scale, const float* shift,
+                              void* out_bf16, int32_t n_images, int32_t H, int32_t W, int32_t c_real, int32_t c_pad,
+                              void* stream) {
+    if (!mel || !w || !bias || !scale || !shift || !out_bf16) return set_error(GD_ERR_INVALID, "gd_speech_stem: null pointer");
+    if (n_images <= 0 || H <= 0 || W <= 0 || c_real <= 0 || c_real > c_pad || c_pad % 8 || c_real > 256)
+        return set_error(GD_ERR_INVALID, "gd_speech_stem: bad shape");
+    const size_t total = (size_t)n_images * H * W * (c_pad / 8);
+    GD_CUDA_CHECK(launch_k(speech_stem_kernel, grid_for(total, 256), 256, (size_t)c_real * 12 * sizeof(float),
+                           reinterpret_cast<cudaStream_t>(stream), 1, mel, w, bias, scale, shift,
+                           reinterpret_cast<__nv_bfloat16*>(out_bf16), n_images, H, W, c_real, c_pad));
+    count_launch();
+    GD_CUDA_CHECK(cudaGetLastError());
+    return GD_OK;
+}
+
+extern "C" int gd_se_gate(const void* y_bf16, int32_t n_images, int32_t grid_h, int32_t grid_w, int32_t c, int32_t c_real,
+                          int32_t c_hidden, const float* w1, const float* b1, const float* w2, const float* b2, float* gate,
+                          void* stream) {
+    if (!y_bf16 || !w1 || !b1 || !w2 || !b2 || !gate) return set_error(GD_ERR_INVALID, "gd_se_gate: null pointer");
+    if (n_images <= 0 || grid_h < 3 || grid_w < 3 || c < 64 || c > 256 || c % 64 || c_real <= 0 || c_real > c ||
+        c_hidden <= 0 || c_hidden > 32)
+        return set_error(GD_ERR_INVALID, "gd_se_gate: bad shape (c in {64,128,192,256}, c_hidden <= 32)");
+    GD_CUDA_CHECK(launch_k(se_gate_kernel, n_images, 256, 0, reinterpret_cast<cudaStream_t>(stream), 1,
+                           reinterpret_cast<const __nv_bfloat16*>(y_bf16), grid_h * grid_w, (grid_h - 2) * (grid_w - 2), c,
+                           c_real, c_hidden, w1, b1, w2, b2, gate));
+    count_launch();
+    GD_CUDA_CHECK(cudaGetLastError());
+    return GD_OK;
+}
+
+extern "C" int gd_se_residual_relu(const void* y_bf16, const void* residual_bf16, const float* gate, void* out_bf16,
+                                   int32_t n_images, int32_t grid_h, int32_t grid_w, int32_t c, void* stream) {
+    if (!y_bf16 || !residual_bf16 || !gate || !out_bf16) return set_error(GD_ERR_INVALID, "gd_se_residual_relu: null pointer");
+    if (n_images <= 0 || grid_h < 3 || grid_w < 3 || c <= 0 || c % 8) return set_error(GD_ERR_INVALID, "gd_se_residual_relu: bad shape");
+    const size_t total = (size_t)n_images * (grid_h - 2) * (grid_w - 2) * (c / 8);
+    GD_CUDA_CHECK(launch_k(se_residual_relu_kernel, grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), 1,
+                           reinterpret_cast<const __nv_bfloat16*>(y_bf16), reinterpret_cast<const __nv_bfloat16*>(residual_bf16),
+                           gate, reinterpret_cast<__nv_bfloat16*>(out_bf16), n_images, grid_h, grid_w, c));
+    count_launch();
+    GD_CUDA_CHECK(cudaGetLastError());
+    return GD_OK;
+}
+
+extern "C" int gd_pixel_shuffle_rows(const void* in_bf16, void* out_bf16, int32_t n_images, int32_t H, int32_t W,
+                                     int32_t c_in, int32_t r, int32_t c_out_pad, void* stream) {
+    if (!in_bf16 || !out_bf16) return set_error(GD_ERR_INVALID, "gd_pixel_shuffle_rows: null pointer");
+    if (n_images <= 0 || H <= 0 || W <= 0 || r < 1 || c_in % (r * r) || c_out_pad % 8 || c_in / (r * r) > c_out_pad)
+        return set_error(GD_ERR_INVALID, "gd_pixel_shuffle_rows: bad shape");
+    const size_t total = (size_t)n_images * H * r * W * r * (c_out_pad / 8);
+    GD_CUDA_CHECK(launch_k(pixel_shuffle_rows_kernel, grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), 1,
+                           reinterpret_cast<const __nv_bfloat16*>(in_bf16), reinterpret_cast<__nv_bfloat16*>(out_bf16), n_images,
+                           H, W, c_in, r, c_out_pad));
+    count_launch();
+    GD_CUDA_CHECK(cudaGetLastError());
+    return GD_OK;
+}

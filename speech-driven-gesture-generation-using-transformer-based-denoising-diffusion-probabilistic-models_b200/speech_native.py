@@ -1,0 +1,236 @@
+"""Once-per-clip speech encoder on our kernels: the ResNetSE-34 trunk and the three pyramid heads of
+`HA2GSpeechEncoder` (reference `models/modules/ha2g/speech_encoder.py:37-61`, `.../model/ResNetSE34V2.py:118-186`,
+`.../model/ResNetBlocks.py:7-37,81-96`) as tensor-core implicit-GEMM convolutions (`gd_conv_taps_bf16`) plus the row
+kernels of csrc/speech_kernels.cu.  The module packs the weights of a `modules.SpeechEncoder` (the state_dict-compatible
+parameter holder) once, owns the feature-map workspace and turns wav (N, T_wav) into the three (N, T_k, d_model)
+feature sequences.
+
+Layout: every feature map is channel-last bf16 "pixel rows" on a zero-bordered grid (include/gd_b200.h); layers narrower
+than 64 channels are zero-padded to 64 (BLOCK_K of the GEMM).  BatchNorm (eval) is folded to a per-channel scale/shift in
+the convolution epilogue; the last Linear of each head (`fc_low/mid/high`) and the shared `wav_proj_layer` are two
+consecutive affine maps and are multiplied together on the host (fp32) into one [d_model, H_k*64] GEMM per head.
+
+Arithmetic: bf16 operands, fp32 accumulation, bf16 feature maps - the same contract as the denoiser's GEMMs.  Every kernel
+treats pixel rows independently and reduces in a fixed order, so a clip's features do not depend on its batch.  The
+mel front end (pre-emphasis, STFT, mel filterbank, InstanceNorm1d) is evaluated by `SpeechEncoder.wav2spec` in fixed
+micro-batches.
+"""
+import ctypes as C
+
+import torch as th
+
+from . import _lib as gd
+
+PAD = 64  # channel granularity of the convolution GEMM (one 128-byte swizzle row of bf16)
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _pad_to(n, m=PAD):
+    return (n + m - 1) // m * m
+
+
+def _fold_bn(bn, c_pad):
+    """eval-mode BatchNorm2d -> (scale, shift) fp32 [c_pad] (padding channels 0)."""
+    scale = (bn.weight.double() / th.sqrt(bn.running_var.double() + bn.eps))
+    shift = bn.bias.double() - bn.running_mean.double() * scale
+    out = th.zeros(2, c_pad, dtype=th.float32, device=bn.weight.device)
+    out[0, :scale.numel()], out[1, :shift.numel()] = scale.float(), shift.float()
+    return out[0].contiguous(), out[1].contiguous()
+
+
+def _pad_vec(v, c_pad):
+    if v is None:
+        return None
+    out = th.zeros(c_pad, dtype=th.float32, device=v.device)
+    out[:v.numel()] = v.float()
+    return out
+
+
+def _pack_conv(weight, ci_pad, co_pad):
+    """(Co, Ci, kh, kw) -> bf16 [co_pad, kh*kw*ci_pad], taps (ky, kx) row-major along K, channels innermost."""
+    co, ci, kh, kw = weight.shape
+    w = th.zeros(co_pad, kh * kw, ci_pad, dtype=th.float32, device=weight.device)
+    w[:co, :, :ci] = weight.float().permute(0, 2, 3, 1).reshape(co, kh * kw, ci)
+    return w.reshape(co_pad, kh * kw * ci_pad).to(th.bfloat16).contiguous()
+
+
+class _Conv:
+    """Packed parameters of one Conv2d [+ReLU] + BatchNorm2d."""
+
+    def __init__(self, conv, bn, relu, ci_pad):
+        self.c_in, self.c_out = ci_pad, _pad_to(conv.out_channels)
+        self.w = _pack_conv(conv.weight.detach(), ci_pad, self.c_out)
+        self.bias = _pad_vec(conv.bias.detach() if conv.bias is not None else None, self.c_out)
+        self.scale, self.shift = _fold_bn(bn, self.c_out)
+        self.relu = int(relu)
+        self.k = conv.kernel_size[0]
+        self.stride = conv.stride[0]
+
+
+class _Block:
+    def __init__(self, blk, ci_pad):
+        self.conv1 = _Conv(blk.conv1, blk.bn1, True, ci_pad)
+        c = self.conv1.c_out
+        self.conv2 = _Conv(blk.conv2, blk.bn2, False, c)
+        self.down = None if blk.downsample is None else _Conv(blk.downsample[0], blk.downsample[1], False, ci_pad)
+        fc1, fc2 = blk.se.fc[0], blk.se.fc[2]
+        self.c, self.c_real, self.c_hidden = c, fc2.out_features, fc1.out_features
+        self.se = [t.detach().float().contiguous() for t in (fc1.weight, fc1.bias, fc2.weight, fc2.bias)]
+
+
+class _Head:
+    """conv_k + ReLU + bn_k, then fc_k and wav_proj_layer merged into one affine map over the [y][c] features of a frame."""
+
+    def __init__(self, conv, bn, fc, proj, shuffle, ci_pad, h_out):
+        self.conv = _Conv(conv, bn, True, ci_pad)
+        self.shuffle, self.h_out = shuffle, h_out
+        cr = conv.out_channels
+        assert fc.in_features == cr * h_out, "pyramid head: fc width does not match the 128-bin mel image"
+        wfc = fc.weight.detach().double().reshape(fc.out_features, cr, h_out).permute(0, 2, 1)  # [o, y, c]
+        wfc_p = th.zeros(fc.out_features, h_out, self.conv.c_out, dtype=th.float64, device=wfc.device)
+        wfc_p[:, :, :cr] = wfc
+        wp = proj.weight.detach().double()
+        self.w = (wp @ wfc_p.reshape(fc.out_features, -1)).to(th.bfloat16).contiguous()      # [d, h_out*c_pad]
+        self.b = (wp @ fc.bias.detach().double() + proj.bias.detach().double()).float().contiguous()
+
+
+class NativeSpeechEncoder:
+    """`SpeechEncoder.forward` on libgd_b200.so.  `chunk` clips go through the trunk at a time (workspace ~8 MB per clip)."""
+
+    MEL_CHUNK = 16  # the mel front end runs in fixed micro-batches (library FFT / matmul pick algorithms per batch size)
+
+    def __init__(self, enc, launcher, device, chunk=64):
+        self.enc, self.L, self.lib, self.dev, self.chunk = enc, launcher, launcher.lib, device, chunk
+        r = enc.wav_encoder.feat_extractor
+        self.d = enc.wav_proj_layer.out_features
+        self.stem_c = r.conv1.out_channels
+        self.stem = [r.conv1.weight.detach().float().reshape(self.stem_c, 9).contiguous(), r.conv1.bias.detach().float().contiguous(),
+                     *[t[:self.stem_c].contiguous() for t in _fold_bn(r.bn1, _pad_to(self.stem_c))]]
+        self.stages, c = [], _pad_to(self.stem_c)
+        for layer in (r.layer1, r.layer2, r.layer3, r.layer4):
+            blocks = []
+            for blk in layer:
+                blocks.append(_Block(blk, c))
+                c = blocks[-1].c
+            self.stages.append(blocks)
+        proj = enc.wav_proj_layer
+        self.heads = [_Head(r.conv_low, r.bn_low, r.fc_low, proj, 1, self.stages[1][0].c, 63),
+                      _Head(r.conv_mid, r.bn_mid, r.fc_mid, proj, 2, PAD, 62),
+                      _Head(r.conv_high, r.bn_high, r.fc_high, proj, 4, PAD, 62)]
+        self._ws = {}
+
+    # ------------------------------------------------------------------ workspace
+    def _workspace(self, n, F):
+        """Buffers for up to `n` clips of F mel frames (zeroed once: the kernels never write a border pixel)."""
+        ws = self._ws.get(F)
+        if ws is not None and ws["cap"] >= n:
+            return ws
+        self._ws.clear()  # one geometry at a time
+        z = lambda rows, c, dt=th.bfloat16: th.zeros(rows, c, device=self.dev, dtype=dt)  # noqa: E731
+        H, W, stages = 128, F, []
+        for s, blocks in enumerate(self.stages):
+            if s > 0:
+                H, W = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+            c, rows = blocks[0].c, n * (H + 2) * (W + 2)
+            stages.append({"H": H, "W": W, "c": c, "x": [z(rows, c), z(rows, c)], "y1": z(rows, c), "y2": z(rows, c),
+                           "r": z(rows, c) if blocks[0].down is not None else None, "gate": z(n, c, th.float32)})
+        heads = []
+        for k, hd in enumerate(self.heads):
+            st = stages[k + 1]
+            gh, gw = st["H"] * hd.shuffle, st["W"] * hd.shuffle
+            w_out = gw - 1 if k == 0 else gw - 2
+            heads.append({"g": None if hd.shuffle == 1 else z(n * gh * gw, PAD), "gh": gh, "gw": gw, "T": w_out,
+                          "feat": z(n * w_out, hd.h_out * hd.conv.c_out), "z": z(n * w_out, self.d, th.float32)})
+        ws = self._ws[F] = {"cap": n, "stages": stages, "heads": heads}
+        return ws
+
+    # ------------------------------------------------------------------ launches
+    def _conv(self, cv, src, n, gh, gw, taps, window, stride, dst, out_strides):
+        d = gd.ConvDesc()
+        d.inp, d.W, d.n_images, d.grid_h, d.grid_w = _p(src), _p(cv.w), n, gh, gw
+        d.c_in, d.c_out, d.n_taps = cv.c_in, cv.c_out, len(taps)
+        for i, t in enumerate(taps):
+            d.tap_shift[i] = t
+        d.bias, d.scale, d.shift, d.relu = _p(cv.bias), _p(cv.scale), _p(cv.shift), cv.relu
+        d.y0, d.y1, d.x0, d.x1 = window
+        d.stride = stride
+        d.out, d.out_ld = _p(dst), cv.c_out
+        d.out_img_stride, d.out_y_stride, d.out_x_stride, d.out_offset = out_strides
+        gd.check(self.lib.gd_conv_taps_bf16(C.byref(d), self.L.stream()), "gd_conv_taps_bf16")
+
+    def _same_conv(self, cv, src, n, src_hw, dst, dst_hw):
+        """k x k convolution with zero 'same' padding (k in {1,3}), stride 1 or 2, between bordered grids."""
+        (H, W), (Ho, Wo) = src_hw, dst_hw
+        gw = W + 2
+        taps = [0] if cv.k == 1 else [(ky - 1) * gw + (kx - 1) for ky in range(3) for kx in range(3)]
+        self._conv(cv, src, n, H + 2, gw, taps, (1, H, 1, W), cv.stride, dst, ((Ho + 2) * (Wo + 2), Wo + 2, 1, Wo + 3))
+
+    def _trunk(self, mel, cap):
+        n, H, F = mel.shape
+        assert H == 128, "the pyramid heads are sized for 128 mel bins"
+        ws, lib, s = self._workspace(cap, F), self.lib, self.L.stream()
+        st = ws["stages"]
+        x = st[0]["x"][0]
+        w, b, sc, sh = self.stem
+        gd.check(lib.gd_speech_stem(_p(mel), _p(w), _p(b), _p(sc), _p(sh), _p(x), n, H, F, self.stem_c, st[0]["c"], s), "gd_speech_stem")
+        prev_hw = (H, F)
+        for si, blocks in enumerate(self.stages):
+            g = st[si]
+            hw, c = (g["H"], g["W"]), g["c"]
+            for bi, blk in enumerate(blocks):
+                in_hw = prev_hw if bi == 0 else hw
+                self._same_conv(blk.conv1, x, n, in_hw, g["y1"], hw)
+                self._same_conv(blk.conv2, g["y1"], n, hw, g["y2"], hw)
+                res = x
+                if blk.down is not None:
+                    self._same_conv(blk.down, x, n, in_hw, g["r"], hw)
+                    res = g["r"]
+                gd.check(lib.gd_se_gate(_p(g["y2"]), n, hw[0] + 2, hw[1] + 2, c, blk.c_real, blk.c_hidden,
+                                        *[_p(t) for t in blk.se], _p(g["gate"]), s), "gd_se_gate")
+                out = g["x"][1] if x is g["x"][0] else g["x"][0]
+                gd.check(lib.gd_se_residual_relu(_p(g["y2"]), _p(res), _p(g["gate"]), _p(out), n, hw[0] + 2, hw[1] + 2, c, s),
+                         "gd_se_residual_relu")
+                x = out
+            g["out"] = x
+            prev_hw = hw
+        outs = []
+        for k, hd in enumerate(self.heads):
+            g, h = st[k + 1], ws["heads"][k]
+            gh, gw, T = h["gh"], h["gw"], h["T"]
+            if hd.shuffle == 1:   # 2x2 valid convolution read straight from the bordered grid
+                gwb = g["W"] + 2
+                self._conv(hd.conv, g["out"], n, g["H"] + 2, gwb, [0, 1, gwb, gwb + 1], (1, g["H"] - 1, 1, g["W"] - 1), 1,
+                           h["feat"], (T * hd.h_out, 1, hd.h_out, 0))
+            else:                 # pixel shuffle to an unbordered grid, then a 3x3 valid convolution
+                gd.check(lib.gd_pixel_shuffle_rows(_p(g["out"]), _p(h["g"]), n, g["H"], g["W"], g["c"], hd.shuffle, PAD, s),
+                         "gd_pixel_shuffle_rows")
+                taps = [(ky - 1) * gw + (kx - 1) for ky in range(3) for kx in range(3)]
+                self._conv(hd.conv, h["g"], n, gh, gw, taps, (1, gh - 2, 1, gw - 2), 1, h["feat"], (T * hd.h_out, 1, hd.h_out, 0))
+            K = hd.h_out * hd.conv.c_out
+            self.L.linear(h["feat"], hd.w, n * T, self.d, K, bias=hd.b, out_f32=h["z"])()
+            outs.append(h["z"][:n * T].view(n, T, self.d))
+        return outs
+
+    def _mel(self, wav):
+        enc, chunk, outs = self.enc, self.MEL_CHUNK, []
+        for lo in range(0, wav.shape[0], chunk):
+            w = wav[lo:lo + chunk].float()
+            n = w.shape[0]
+            if n < chunk:
+                w = th.cat([w, w.new_zeros(chunk - n, w.shape[1])], dim=0)
+            outs.append(enc.mel_spec_norm(enc.wav2spec(w) + 1e-6)[:n])
+        return th.cat(outs, dim=0).contiguous()
+
+    @th.no_grad()
+    def __call__(self, wav):
+        """wav (N, T_wav) on the device -> (z_low, z_mid, z_high), fp32 (N, T_k, d_model)."""
+        mel = self._mel(wav)
+        outs = [[], [], []]
+        cap = min(self.chunk, mel.shape[0])
+        for lo in range(0, mel.shape[0], self.chunk):
+            for k, z in enumerate(self._trunk(mel[lo:lo + self.chunk], cap)):
+                outs[k].append(z.clone())
+        return tuple(th.cat(o, dim=0) for o in outs)

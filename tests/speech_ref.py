@@ -1,0 +1,145 @@
+"""Plain-torch statements of the speech-encoder entry points of include/gd_b200.h (test infrastructure).
+
+Two uses: (1) on the GPU the real kernels are compared with these on the same descriptors; (2) on CPU `FakeLib` stands in
+for libgd_b200.so so that the host logic of gesture_b200.speech_native (weight packing, grid geometry, tap shifts, head
+merge) is checked end to end against the fp32 `SpeechEncoder` module without a GPU.  bf16 storage is emulated by rounding.
+"""
+import torch as th
+
+
+def bf16_round(t):
+    return t.to(th.bfloat16).float()
+
+
+def conv_taps_ref(inp, W, n_images, grid_h, grid_w, taps, bias, scale, shift, relu, window, stride, out, out_strides):
+    """gd_conv_taps_bf16 on tensors: inp [rows, c_in], W [c_out, n_taps*c_in], out [*, c_out] modified in place."""
+    rows, c_in = n_images * grid_h * grid_w, inp.shape[1]
+    A = inp[:rows].float()
+    Wf = W.float()
+    acc = th.zeros(rows, W.shape[0], dtype=th.float32, device=inp.device)
+    for t, sh in enumerate(taps):
+        shifted = th.zeros_like(A)
+        lo, hi = max(0, -sh), min(rows, rows - sh)
+        if hi > lo:
+            shifted[lo:hi] = A[lo + sh:hi + sh]
+        acc += shifted @ Wf[:, t * c_in:(t + 1) * c_in].T
+    if bias is not None:
+        acc = acc + bias
+    if relu:
+        acc = acc.clamp_min(0)
+    acc = acc * scale + shift
+    r = th.arange(rows, device=inp.device)
+    img, rem = r // (grid_h * grid_w), r % (grid_h * grid_w)
+    y, x = rem // grid_w, rem % grid_w
+    y0, y1, x0, x1 = window
+    keep = (y >= y0) & (y <= y1) & (x >= x0) & (x <= x1) & ((y - y0) % stride == 0) & ((x - x0) % stride == 0)
+    si, sy, sx, off = out_strides
+    orow = img * si + ((y - y0) // stride) * sy + ((x - x0) // stride) * sx + off
+    out[orow[keep]] = acc[keep].to(out.dtype)
+    return out
+
+
+def stem_ref(mel, w, bias, scale, shift, out, c_pad):
+    """gd_speech_stem: mel (n, H, W) fp32 -> bordered channel-last rows [n*(H+2)*(W+2), c_pad]."""
+    n, H, W = mel.shape
+    c = w.shape[0]
+    y = th.nn.functional.conv2d(mel[:, None], w.view(c, 1, 3, 3), bias, padding=1).clamp_min(0)
+    y = y * scale[None, :, None, None] + shift[None, :, None, None]
+    grid = out[:n * (H + 2) * (W + 2)].view(n, H + 2, W + 2, c_pad)
+    grid[:, 1:H + 1, 1:W + 1, :c] = y.permute(0, 2, 3, 1).to(out.dtype)
+    grid[:, 1:H + 1, 1:W + 1, c:] = 0
+    return out
+
+
+def se_gate_ref(y, n_images, grid_h, grid_w, c_real, w1, b1, w2, b2, gate):
+    c = y.shape[1]
+    g = y[:n_images * grid_h * grid_w].float().view(n_images, grid_h * grid_w, c)
+    mean = g.sum(dim=1)[:, :c_real] / ((grid_h - 2) * (grid_w - 2))
+    a = th.sigmoid(th.relu(mean @ w1.T + b1) @ w2.T + b2)
+    gate[:n_images] = 0
+    gate[:n_images, :c_real] = a
+    return gate
+
+
+def se_residual_relu_ref(y, res, gate, out, n_images, grid_h, grid_w):
+    c = y.shape[1]
+    rows = n_images * grid_h * grid_w
+    v = lambda t: t[:rows].view(n_images, grid_h, grid_w, c)  # noqa: E731
+    o = th.relu(gate[:n_images, None, None, :] * v(y).float() + v(res).float())
+    v(out)[:, 1:-1, 1:-1] = o[:, 1:-1, 1:-1].to(out.dtype)
+    return out
+
+
+def pixel_shuffle_ref(inp, out, n_images, H, W, r, c_out_pad):
+    c_in = inp.shape[1]
+    feat = inp[:n_images * (H + 2) * (W + 2)].view(n_images, H + 2, W + 2, c_in)[:, 1:-1, 1:-1].permute(0, 3, 1, 2)
+    sh = th.nn.functional.pixel_shuffle(feat.float(), r)  # (n, c_in/r^2, H*r, W*r)
+    o = out[:n_images * H * r * W * r].view(n_images, H * r, W * r, c_out_pad)
+    o.zero_()
+    o[..., :sh.shape[1]] = sh.permute(0, 2, 3, 1).to(out.dtype)
+    return out
+
+
+class FakeLauncher:
+    """Stands in for engine._Launcher + libgd_b200.so on CPU: every 'kernel' is the torch statement above.  Tensors are
+    found through the pointers the host code puts into the descriptors (registered by `track`)."""
+
+    def __init__(self):
+        self.lib = self
+        self.tensors = {}
+        self.calls = []
+
+    def track(self, t):
+        if t is not None:
+            self.tensors[t.data_ptr()] = t
+        return None if t is None else t.data_ptr()
+
+    def _t(self, ptr):
+        return None if not ptr else self.tensors[ptr]
+
+    @staticmethod
+    def stream():
+        return None
+
+    def linear(self, A, W, M, N, K, bias=None, out_f32=None, **kw):
+        assert not kw and A.shape[1] == K and W.shape == (N, K)
+
+        def run():
+            self.calls.append("gd_linear_bf16")
+            out_f32[:M] = A[:M].float() @ W.float().T + bias
+        return run
+
+    def gd_conv_taps_bf16(self, ref, stream):
+        d = ref._obj
+        self.calls.append("gd_conv_taps_bf16")
+        inp, W, out = self._t(d.inp), self._t(d.W), self._t(d.out)
+        assert inp.shape[1] == d.c_in and W.shape == (d.c_out, d.n_taps * d.c_in) and d.out_ld == d.c_out
+        out2 = out.view(-1, d.c_out)
+        conv_taps_ref(inp, W, d.n_images, d.grid_h, d.grid_w, [d.tap_shift[i] for i in range(d.n_taps)], self._t(d.bias),
+                      self._t(d.scale), self._t(d.shift), d.relu, (d.y0, d.y1, d.x0, d.x1), d.stride, out2,
+                      (d.out_img_stride, d.out_y_stride, d.out_x_stride, d.out_offset))
+        return 0
+
+    def gd_speech_stem(self, mel, w, b, sc, sh, out, n, H, W, c_real, c_pad, stream):
+        self.calls.append("gd_speech_stem")
+        stem_ref(self._t(mel)[:n], self._t(w), self._t(b), self._t(sc), self._t(sh), self._t(out), c_pad)
+        return 0
+
+    def gd_se_gate(self, y, n, gh, gw, c, c_real, c_hidden, w1, b1, w2, b2, gate, stream):
+        self.calls.append("gd_se_gate")
+        assert self._t(w1).shape == (c_hidden, c_real)
+        se_gate_ref(self._t(y), n, gh, gw, c_real, self._t(w1), self._t(b1), self._t(w2), self._t(b2), self._t(gate))
+        return 0
+
+    def gd_se_residual_relu(self, y, res, gate, out, n, gh, gw, c, stream):
+        self.calls.append("gd_se_residual_relu")
+        se_residual_relu_ref(self._t(y), self._t(res), self._t(gate), self._t(out), n, gh, gw)
+        return 0
+
+    def gd_pixel_shuffle_rows(self, inp, out, n, H, W, c_in, r, c_out_pad, stream):
+        self.calls.append("gd_pixel_shuffle_rows")
+        pixel_shuffle_ref(self._t(inp), self._t(out), n, H, W, r, c_out_pad)
+        return 0
+
+    def gd_last_error(self):
+        return b""

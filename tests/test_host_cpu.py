@@ -25,7 +25,7 @@ def test_cabi_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), f"{name} not exported by libgd_b200.so"
-    assert _lib.load().gd_abi_version() == 2
+    assert _lib.load().gd_abi_version() == 3
     assert _lib.load().gd_launch_count() == 0 or _lib.load().gd_launch_count() > 0
 
 

@@ -1,0 +1,172 @@
+"""GPU parity of the once-per-clip speech encoder: each kernel of include/gd_b200.h's speech section against its plain
+torch statement (tests/speech_ref.py), then the whole native encoder against the fp32 `SpeechEncoder` module."""
+import ctypes as C
+import math
+
+import pytest
+import torch as th
+
+import speech_ref as ref
+from test_speech_host_cpu import randomise_batchnorm
+
+pytestmark = pytest.mark.gpu
+
+
+def _stream():
+    return th.cuda.current_stream().cuda_stream
+
+
+def _conv(gd, inp, W, n, gh, gw, taps, bias, scale, shift, relu, window, stride, out, out_strides):
+    d = gd.ConvDesc()
+    d.inp, d.W, d.n_images, d.grid_h, d.grid_w = inp.data_ptr(), W.data_ptr(), n, gh, gw
+    d.c_in, d.c_out, d.n_taps = inp.shape[1], W.shape[0], len(taps)
+    for i, t in enumerate(taps):
+        d.tap_shift[i] = t
+    d.bias, d.scale, d.shift, d.relu = gd.ptr(bias), scale.data_ptr(), shift.data_ptr(), int(relu)
+    d.y0, d.y1, d.x0, d.x1 = window
+    d.stride = stride
+    d.out, d.out_ld = out.data_ptr(), out.shape[1]
+    d.out_img_stride, d.out_y_stride, d.out_x_stride, d.out_offset = out_strides
+    gd.check(gd.load().gd_conv_taps_bf16(C.byref(d), _stream()), "gd_conv_taps_bf16")
+    th.cuda.synchronize()
+
+
+def _bordered(n, H, W, c, g, c_real=None):
+    """random bf16 feature map on a zero-bordered grid, channels >= c_real zero."""
+    x = th.zeros(n, H + 2, W + 2, c, device="cuda")
+    x[:, 1:-1, 1:-1, :c_real or c] = th.randn(n, H, W, c_real or c, device="cuda", generator=g)
+    return x.reshape(-1, c).bfloat16()
+
+
+@pytest.mark.parametrize("n,H,W,ci,co,k,stride,relu,with_bias", [
+    (3, 16, 9, 64, 64, 3, 1, True, False),      # layer1-like block convolution
+    (2, 16, 9, 64, 128, 3, 2, True, False),     # first convolution of a stage (stride 2)
+    (2, 16, 9, 64, 128, 1, 2, False, False),    # its 1x1 down-sample branch
+    (5, 12, 7, 128, 256, 3, 1, False, True),    # wide output tile, bias
+    (70, 32, 16, 128, 128, 3, 1, False, False),  # enough m-tiles for the 128-wide tile path (>= 148)
+    (40, 16, 8, 256, 256, 3, 1, True, False),   # long K (2304), 256-wide tiles
+])
+def test_conv_taps_same_padding(gd, n, H, W, ci, co, k, stride, relu, with_bias):
+    g = th.Generator(device="cuda").manual_seed(n * 100 + ci + co + k)
+    x = _bordered(n, H, W, ci, g)
+    w4 = th.randn(co, ci, k, k, device="cuda", generator=g) / math.sqrt(ci * k * k)
+    Wp = w4.permute(0, 2, 3, 1).reshape(co, k * k * ci).bfloat16().contiguous()
+    bias = th.randn(co, device="cuda", generator=g) if with_bias else None
+    scale = th.rand(co, device="cuda", generator=g) + 0.5
+    shift = th.randn(co, device="cuda", generator=g) * 0.1
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    gw = W + 2
+    taps = [0] if k == 1 else [(ky - 1) * gw + (kx - 1) for ky in range(3) for kx in range(3)]
+    geo = ((Ho + 2) * (Wo + 2), Wo + 2, 1, Wo + 3)
+    out = th.full((n * (Ho + 2) * (Wo + 2), co), 7.0, device="cuda", dtype=th.bfloat16)
+    _conv(gd, x, Wp, n, H + 2, gw, taps, bias, scale, shift, relu, (1, H, 1, W), stride, out, geo)
+    want = th.full_like(out, 7.0)
+    ref.conv_taps_ref(x, Wp, n, H + 2, gw, taps, bias, scale, shift, relu, (1, H, 1, W), stride, want, geo)
+    # independent statement: F.conv2d on the same bf16-rounded operands
+    img = x.float().view(n, H + 2, W + 2, ci)[:, 1:-1, 1:-1].permute(0, 3, 1, 2)
+    y = th.nn.functional.conv2d(img, Wp.float().view(co, k, k, ci).permute(0, 3, 1, 2), bias, stride=stride, padding=k // 2)
+    y = (y.clamp_min(0) if relu else y) * scale[None, :, None, None] + shift[None, :, None, None]
+    got = out.view(n, Ho + 2, Wo + 2, co)
+    assert (got[:, 1:-1, 1:-1].float() - y.permute(0, 2, 3, 1)).abs().max().item() < 3e-2
+    assert (out.float() - want.float()).abs().max().item() < 3e-2
+    border = th.ones(Ho + 2, Wo + 2, dtype=th.bool, device="cuda")
+    border[1:-1, 1:-1] = False
+    assert (got[:, border] == 7.0).all(), "border pixels must never be written"
+
+
+def test_conv_taps_valid_head_layout(gd):
+    """3x3 valid convolution on an unbordered grid, output transposed to [image][x][y][c] (the pyramid heads)."""
+    n, gh, gw, c = 3, 20, 12, 64
+    g = th.Generator(device="cuda").manual_seed(3)
+    x = th.randn(n * gh * gw, c, device="cuda", generator=g).bfloat16()
+    w4 = th.randn(c, c, 3, 3, device="cuda", generator=g) / math.sqrt(9 * c)
+    Wp = w4.permute(0, 2, 3, 1).reshape(c, 9 * c).bfloat16().contiguous()
+    bias, scale, shift = (th.randn(c, device="cuda", generator=g) for _ in range(3))
+    T, hh = gw - 2, gh - 2
+    out = th.zeros(n * T * hh, c, device="cuda", dtype=th.bfloat16)
+    taps = [(ky - 1) * gw + (kx - 1) for ky in range(3) for kx in range(3)]
+    _conv(gd, x, Wp, n, gh, gw, taps, bias, scale, shift, True, (1, gh - 2, 1, gw - 2), 1, out, (T * hh, 1, hh, 0))
+    img = x.float().view(n, gh, gw, c).permute(0, 3, 1, 2)
+    y = th.nn.functional.conv2d(img, Wp.float().view(c, 3, 3, c).permute(0, 3, 1, 2), bias).clamp_min(0)
+    y = y * scale[None, :, None, None] + shift[None, :, None, None]          # (n, c, hh, T)
+    assert (out.view(n, T, hh, c).float() - y.permute(0, 3, 2, 1)).abs().max().item() < 4e-2
+
+
+def test_conv_taps_rejects_bad_arguments(gd):
+    x = th.zeros(100, 64, device="cuda", dtype=th.bfloat16)
+    w = th.zeros(64, 64, device="cuda", dtype=th.bfloat16)
+    v = th.zeros(64, device="cuda")
+    with pytest.raises(gd.GdError):
+        _conv(gd, x[:, :32].contiguous(), w, 1, 10, 10, [0], None, v, v, False, (1, 8, 1, 8), 1, x, (100, 10, 1, 11))
+    with pytest.raises(gd.GdError):
+        _conv(gd, x, w, 1, 10, 10, [0], None, v, v, False, (1, 10, 1, 8), 1, x, (100, 10, 1, 11))  # window outside grid
+    with pytest.raises(gd.GdError):
+        _conv(gd, x, w, 1, 10, 10, [0], None, v, v, False, (1, 8, 1, 8), 3, x, (100, 10, 1, 11))   # stride 3
+
+
+def test_stem_gate_tail_shuffle(gd):
+    lib = gd.load()
+    g = th.Generator(device="cuda").manual_seed(11)
+    n, H, W, c_real, c = 3, 128, 13, 32, 64
+    mel = th.randn(n, H, W, device="cuda", generator=g)
+    w, b = th.randn(c_real, 9, device="cuda", generator=g) / 3, th.randn(c_real, device="cuda", generator=g)
+    sc, sh = th.rand(c_real, device="cuda", generator=g) + 0.5, th.randn(c_real, device="cuda", generator=g)
+    out = th.zeros(n * (H + 2) * (W + 2), c, device="cuda", dtype=th.bfloat16)
+    gd.check(lib.gd_speech_stem(mel.data_ptr(), w.data_ptr(), b.data_ptr(), sc.data_ptr(), sh.data_ptr(), out.data_ptr(),
+                                n, H, W, c_real, c, _stream()), "gd_speech_stem")
+    want = ref.stem_ref(mel, w, b, sc, sh, th.zeros_like(out), c)
+    assert (out.float() - want.float()).abs().max().item() < 3e-2
+
+    # squeeze-excite gate on that map (32 real channels, hidden 4) and on a 256-channel map
+    for (y, gh, gw, cc, cr) in [(out, H + 2, W + 2, c, c_real), (_bordered(4, 16, 8, 256, g), 18, 10, 256, 256)]:
+        ch, ni = cr // 8, y.shape[0] // (gh * gw)
+        w1, b1 = th.randn(ch, cr, device="cuda", generator=g) / math.sqrt(cr), th.randn(ch, device="cuda", generator=g)
+        w2, b2 = th.randn(cr, ch, device="cuda", generator=g) / math.sqrt(ch), th.randn(cr, device="cuda", generator=g)
+        gate = th.full((ni, cc), -1.0, device="cuda")
+        gd.check(lib.gd_se_gate(y.data_ptr(), ni, gh, gw, cc, cr, ch, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                                b2.data_ptr(), gate.data_ptr(), _stream()), "gd_se_gate")
+        want_gate = ref.se_gate_ref(y, ni, gh, gw, cr, w1, b1, w2, b2, th.zeros_like(gate))
+        assert (gate - want_gate).abs().max().item() < 1e-4
+        # block tail
+        res = _bordered(ni, gh - 2, gw - 2, cc, g, cr)
+        o = th.full_like(y, 5.0)
+        gd.check(lib.gd_se_residual_relu(y.data_ptr(), res.data_ptr(), gate.data_ptr(), o.data_ptr(), ni, gh, gw, cc,
+                                         _stream()), "gd_se_residual_relu")
+        want_o = ref.se_residual_relu_ref(y, res, want_gate, th.full_like(y, 5.0), ni, gh, gw)
+        assert (o.float() - want_o.float()).abs().max().item() < 3e-2
+        assert (o.view(ni, gh, gw, cc)[:, 0] == 5.0).all() and (o.view(ni, gh, gw, cc)[:, :, -1] == 5.0).all()
+
+    # pixel shuffles of the mid / high heads
+    for (Hs, Ws, ci, r) in [(32, 5, 128, 2), (16, 3, 256, 4)]:
+        x = _bordered(2, Hs, Ws, ci, g)
+        o = th.full((2 * Hs * r * Ws * r, 64), 9.0, device="cuda", dtype=th.bfloat16)
+        gd.check(lib.gd_pixel_shuffle_rows(x.data_ptr(), o.data_ptr(), 2, Hs, Ws, ci, r, 64, _stream()), "gd_pixel_shuffle_rows")
+        want_s = ref.pixel_shuffle_ref(x, th.zeros_like(o), 2, Hs, Ws, r, 64)
+        assert th.equal(o, want_s)
+
+
+@pytest.mark.parametrize("d_model,n,wav_len,chunk", [(256, 5, 32000, 4), (512, 3, 36266, 64), (256, 2, 128000, 64)])
+def test_native_encoder_matches_fp32_module(gd, d_model, n, wav_len, chunk):
+    from gesture_b200.engine import _Launcher
+    from gesture_b200.modules import SpeechEncoder
+    from gesture_b200.speech_native import NativeSpeechEncoder
+    th.manual_seed(0)
+    enc = SpeechEncoder(d_model).eval()
+    randomise_batchnorm(enc)
+    enc.cuda()
+    wav = th.randn(n, wav_len, device="cuda", generator=th.Generator(device="cuda").manual_seed(4))
+    prev = th.backends.cudnn.allow_tf32, th.backends.cuda.matmul.allow_tf32
+    th.backends.cudnn.allow_tf32 = th.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with th.no_grad():
+            want = enc(wavform=wav)
+        native = NativeSpeechEncoder(enc, _Launcher(), th.device("cuda", 0), chunk=chunk)
+        got = native(wav)
+        again = native(wav[n - 1:])          # another batch composition: bit-identical per clip
+    finally:
+        th.backends.cudnn.allow_tf32, th.backends.cuda.matmul.allow_tf32 = prev
+    for a, b, c in zip(want, got, again):
+        assert a.shape == b.shape
+        rel = ((a - b).norm() / a.norm()).item()
+        assert rel < 2e-2, rel   # bf16 operands / feature maps, fp32 accumulation; measured 5e-3 - 8e-3
+        assert th.equal(b[n - 1:], c)
