@@ -222,25 +222,34 @@ int gd_cast_rows_bf16(const float* src, int32_t lds, void* dst, int32_t ldd, int
  * trunk `models/modules/ha2g/model/ResNetSE34V2.py:118-186` with SEBasicBlock / SELayer `.../ResNetBlocks.py:7-37,81-96`.
  *
  * Feature maps are channel-last bf16 "pixel rows" over a zero-bordered grid: row = image*(grid_h*grid_w) + y*grid_w + x,
- * C channels contiguous (C % 64 == 0; narrower layers are zero-padded to 64).  The border pixels are never written, so a
- * buffer zeroed once keeps supplying the convolutions' zero padding.
+ * c channels contiguous - one bf16 plane [c] (`split` = 0) or two planes [hi(c) | lo(c)] with value = hi + lo
+ * (`split` = 1, ~16 mantissa bits).  The border pixels are never written, so a buffer zeroed once keeps supplying the
+ * convolutions' zero padding.
  *
  * gd_conv_taps_bf16: nn.Conv2d (+ bias) [+ ReLU] + eval-mode BatchNorm2d as one implicit GEMM on the tensor cores:
  *
- *   acc[row, co] = sum_tap sum_ci W[co, tap*c_in + ci] * in[row + tap_shift[tap], ci]        (rows outside the tensor read 0)
+ *   acc[row, co] = sum_tap sum_{k < k_per_tap} W[co, tap*k_per_tap + k] * in[row + tap_shift[tap], k mod in_ld]   (rows outside read 0)
  *   v            = (relu ? max(acc + bias, 0) : acc + bias) * scale + shift                  (scale/shift = folded BatchNorm)
  *
  * stored as bf16 for the pixels with y0 <= y <= y1, x0 <= x <= x1 whose (y - y0, x - x0) are multiples of `stride`, at
  * output row  image*out_img_stride + ((y-y0)/stride)*out_y_stride + ((x-x0)/stride)*out_x_stride + out_offset.
  * A 3x3 "same" convolution on a bordered grid is tap_shift = (ky-1)*grid_w + (kx-1) over the interior; a stride-2
  * convolution is the same accumulation keeping every other pixel (ResNetSE34V2.py:96-112 `_make_layer`).
+ *
+ * Split precision (the default of the encoder): a feature map row holds two bf16 planes [hi(c) | lo(c)], value = hi + lo
+ * (~16 mantissa bits).  The K walk of a tap wraps around the input row (k mod in_ld), so with k_per_tap = 3c the operand
+ * sequence is hi, lo, hi; the host packs W per tap as [Whi | Whi | Wlo] and the GEMM accumulates
+ * hi*Whi + lo*Whi + hi*Wlo in fp32 - the bf16x3 product, whose dropped term lo*Wlo is ~2^-18 relative.  With split_out
+ * the epilogue stores channels [0, c_store) as [hi(c_store) | lo(c_store)].  Plain bf16: in_ld = k_per_tap = c_in.
  * ------------------------------------------------------------------------------------------ */
 #define GD_CONV_MAX_TAPS 9
 typedef struct gd_conv_desc {
-    const void* in;      /* bf16 [n_images*grid_h*grid_w, c_in]                                */
-    const void* W;       /* bf16 [c_out, n_taps*c_in]                                           */
+    const void* in;      /* bf16 [n_images*grid_h*grid_w, in_ld]                                */
+    const void* W;       /* bf16 [c_out, n_taps*k_per_tap]                                      */
     int32_t n_images, grid_h, grid_w;
-    int32_t c_in, c_out; /* multiples of 64                                                     */
+    int32_t in_ld;       /* input row width (elements), multiple of 64                          */
+    int32_t k_per_tap;   /* K elements per tap, multiple of 64                                  */
+    int32_t c_out;       /* GEMM N: multiple of 64                                              */
     int32_t n_taps;
     int32_t tap_shift[GD_CONV_MAX_TAPS];
     const float* bias;   /* [c_out] or NULL                                                     */
@@ -251,6 +260,8 @@ typedef struct gd_conv_desc {
     void* out;           /* bf16 rows of out_ld elements                                        */
     int32_t out_ld;
     int32_t out_img_stride, out_y_stride, out_x_stride, out_offset;
+    int32_t c_store;     /* output channels stored (multiple of 32, <= c_out)                   */
+    int32_t split_out;   /* 0: [c_store] bf16;  1: [hi(c_store) | lo(c_store)]                  */
 } gd_conv_desc;
 
 int gd_conv_taps_bf16(const gd_conv_desc* d, void* stream);
@@ -259,24 +270,25 @@ int gd_conv_taps_bf16(const gd_conv_desc* d, void* stream);
  * mel fp32 (n_images, H, W) -> bf16 pixel rows on the (H+2) x (W+2) bordered grid, channels [c_real, c_pad) written as 0.
  *   w fp32 [c_real, 9], bias / scale / shift fp32 [c_real]. */
 int gd_speech_stem(const float* mel, const float* w, const float* bias, const float* scale, const float* shift,
-                   void* out_bf16, int32_t n_images, int32_t H, int32_t W, int32_t c_real, int32_t c_pad, void* stream);
+                   void* out_bf16, int32_t n_images, int32_t H, int32_t W, int32_t c_real, int32_t c_pad, int32_t split,
+                   void* stream);
 
 /* SELayer gate (ResNetBlocks.py:81-96): gate[img, c] = sigmoid(W2 · relu(W1 · mean_pixels(y[img]) + b1) + b2).
  * y: bf16 pixel rows on a bordered grid (border = 0), `c` channels per row of which the first c_real are real;
  * w1 fp32 [c_hidden, c_real], w2 fp32 [c_real, c_hidden]; gate fp32 [n_images, c] (padding channels get 0).
  * Fixed summation order per image: the gate of a clip does not depend on the batch it is in. */
-int gd_se_gate(const void* y_bf16, int32_t n_images, int32_t grid_h, int32_t grid_w, int32_t c, int32_t c_real,
+int gd_se_gate(const void* y_bf16, int32_t n_images, int32_t grid_h, int32_t grid_w, int32_t c, int32_t split, int32_t c_real,
                int32_t c_hidden, const float* w1, const float* b1, const float* w2, const float* b2, float* gate,
                void* stream);
 
 /* Block tail (ResNetBlocks.py:30-36): out = relu(gate[img, c] * y + residual) on the interior pixels of the grid. */
 int gd_se_residual_relu(const void* y_bf16, const void* residual_bf16, const float* gate, void* out_bf16,
-                        int32_t n_images, int32_t grid_h, int32_t grid_w, int32_t c, void* stream);
+                        int32_t n_images, int32_t grid_h, int32_t grid_w, int32_t c, int32_t split, void* stream);
 
 /* nn.PixelShuffle(r) (ResNetSE34V2.py:169-170,181-182) from a bordered grid (H+2) x (W+2) with c_in channels to an
  * unbordered (H*r) x (W*r) grid with c_in/r^2 real channels zero-padded to c_out_pad. */
 int gd_pixel_shuffle_rows(const void* in_bf16, void* out_bf16, int32_t n_images, int32_t H, int32_t W, int32_t c_in,
-                          int32_t r, int32_t c_out_pad, void* stream);
+                          int32_t r, int32_t c_out_pad, int32_t split, void* stream);
 
 /* *step_ptr += delta (one thread) — closes a denoise step inside a captured graph. */
 int gd_step_add(int32_t* step_ptr, int32_t delta, void* stream);

@@ -42,10 +42,11 @@ class AttnDesc(C.Structure):
 
 class ConvDesc(C.Structure):
     _fields_ = [("inp", c_vp), ("W", c_vp), ("n_images", c_i32), ("grid_h", c_i32), ("grid_w", c_i32),
-                ("c_in", c_i32), ("c_out", c_i32), ("n_taps", c_i32), ("tap_shift", c_i32 * 9), ("bias", c_vp),
-                ("scale", c_vp), ("shift", c_vp), ("relu", c_i32), ("y0", c_i32), ("y1", c_i32), ("x0", c_i32),
-                ("x1", c_i32), ("stride", c_i32), ("out", c_vp), ("out_ld", c_i32), ("out_img_stride", c_i32),
-                ("out_y_stride", c_i32), ("out_x_stride", c_i32), ("out_offset", c_i32)]
+                ("in_ld", c_i32), ("k_per_tap", c_i32), ("c_out", c_i32), ("n_taps", c_i32), ("tap_shift", c_i32 * 9),
+                ("bias", c_vp), ("scale", c_vp), ("shift", c_vp), ("relu", c_i32), ("y0", c_i32), ("y1", c_i32),
+                ("x0", c_i32), ("x1", c_i32), ("stride", c_i32), ("out", c_vp), ("out_ld", c_i32),
+                ("out_img_stride", c_i32), ("out_y_stride", c_i32), ("out_x_stride", c_i32), ("out_offset", c_i32),
+                ("c_store", c_i32), ("split_out", c_i32)]
 
 
 ACT_NONE, ACT_RELU2, ACT_SILU = 0, 1, 2
@@ -69,10 +70,10 @@ SYMBOLS = {
     "gd_cast_rows_bf16": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "gd_step_add": (c_i32, [c_vp, c_i32, c_vp]),
     "gd_conv_taps_bf16": (c_i32, [C.POINTER(ConvDesc), c_vp]),
-    "gd_speech_stem": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
-    "gd_se_gate": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "gd_se_residual_relu": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
-    "gd_pixel_shuffle_rows": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "gd_speech_stem": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "gd_se_gate": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gd_se_residual_relu": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "gd_pixel_shuffle_rows": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
 }
 
 

@@ -46,8 +46,9 @@ struct GemmParams {
     int ldo_bf16;
     int reduce_add;  // MODE_TMA_F32: 1 = out += result (in-place residual), 0 = out = result
     gd_ddpm_desc ddpm;
-    // MODE_CONV: k-block kb reads A rows m0 + tap_shift[kb / kb_per_tap], columns (kb % kb_per_tap) * 64
-    int kb_per_tap;
+    // MODE_CONV: k-block kb reads A rows m0 + tap_shift[kb / kb_per_tap], columns ((kb % kb_per_tap) * 64) mod a_cols
+    int kb_per_tap, a_cols;
+    int split_out, c_store;  // split_out: channels [0, c_store) stored as [hi(c_store) | lo(c_store)] bf16 pairs
     int tap_shift[GD_CONV_MAX_TAPS];
     const float* scale;   // per output channel, applied after bias (+ReLU): folded BatchNorm
     const float* shift;
@@ -170,14 +171,19 @@ __device__ __forceinline__ void epilogue_conv_chunk(const GemmParams& p, size_t 
         r[4 * j + 3] = fmaf(r[4 * j + 3], sc.w, sh.w);
     }
     uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + out_row * p.ldo_bf16 + col0);
+    uint32_t hi[16];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        uint4 w;
-        w.x = pack_bf16x2(r[8 * j + 0], r[8 * j + 1]);
-        w.y = pack_bf16x2(r[8 * j + 2], r[8 * j + 3]);
-        w.z = pack_bf16x2(r[8 * j + 4], r[8 * j + 5]);
-        w.w = pack_bf16x2(r[8 * j + 6], r[8 * j + 7]);
-        o4[j] = w;
+    for (int j = 0; j < 16; ++j) hi[j] = pack_bf16x2(r[2 * j], r[2 * j + 1]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o4[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+    if (p.split_out) {  // second bf16 plane: what the first one lost (v = hi + lo to ~2^-17)
+        uint32_t lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            lo[j] = pack_bf16x2(r[2 * j] - __uint_as_float(hi[j] << 16), r[2 * j + 1] - __uint_as_float(hi[j] & 0xffff0000u));
+        uint4* l4 = o4 + (p.c_store >> 3);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) l4[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
     }
 }
 
@@ -329,7 +335,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         int a_col = kb * BLOCK_K, a_row = m0;
                         if (MODE == MODE_CONV) {  // tap-shifted pixel rows; rows outside [0, M) are zero-filled by TMA
                             const int tap = kb / p.kb_per_tap;
-                            a_col = (kb - tap * p.kb_per_tap) * BLOCK_K;
+                            a_col = ((kb - tap * p.kb_per_tap) * BLOCK_K) % p.a_cols;  // wraps: split rows are walked hi, lo, hi
                             a_row = m0 + p.tap_shift[tap];
                         }
                         tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_a, &full_bar[stage], a_col, a_row);
@@ -564,7 +570,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 } else if (MODE == MODE_CONV) {
                     tmem_ld_wait();
                     if (c == WCOLS / 32 - 1) release_accumulator();
-                    if (conv_keep) epilogue_conv_chunk(p, conv_out_row, col0, v);
+                    if (conv_keep && col0 < p.c_store) epilogue_conv_chunk(p, conv_out_row, col0, v);
                 } else {
                     tmem_ld_wait();
                     if (row < p.M) {
@@ -778,13 +784,17 @@ extern "C" int gd_conv_taps_bf16(const gd_conv_desc* d, void* stream) {
     if (!d || !d->in || !d->W || !d->out || !d->scale || !d->shift)
         return set_error(GD_ERR_INVALID, "gd_conv_taps_bf16: null descriptor/operand");
     if (d->n_images <= 0 || d->grid_h <= 0 || d->grid_w <= 0) return set_error(GD_ERR_INVALID, "gd_conv_taps_bf16: empty grid");
-    if (d->c_in <= 0 || d->c_in % BLOCK_K || d->c_out <= 0 || d->c_out % 64)
-        return set_error(GD_ERR_INVALID, "gd_conv_taps_bf16: c_in=%d / c_out=%d must be multiples of 64", d->c_in, d->c_out);
+    if (d->in_ld <= 0 || d->in_ld % BLOCK_K || d->k_per_tap <= 0 || d->k_per_tap % BLOCK_K || d->c_out <= 0 || d->c_out % 64)
+        return set_error(GD_ERR_INVALID, "gd_conv_taps_bf16: in_ld=%d / k_per_tap=%d / c_out=%d must be multiples of 64", d->in_ld,
+                         d->k_per_tap, d->c_out);
+    if (d->c_store <= 0 || d->c_store % 32 || d->c_store > d->c_out)
+        return set_error(GD_ERR_INVALID, "gd_conv_taps_bf16: c_store=%d must be a multiple of 32 and <= c_out", d->c_store);
     if (d->n_taps < 1 || d->n_taps > GD_CONV_MAX_TAPS) return set_error(GD_ERR_INVALID, "gd_conv_taps_bf16: n_taps out of range");
     if (d->stride != 1 && d->stride != 2) return set_error(GD_ERR_INVALID, "gd_conv_taps_bf16: stride must be 1 or 2");
     if (d->y0 < 0 || d->y1 >= d->grid_h || d->x0 < 0 || d->x1 >= d->grid_w || d->y0 > d->y1 || d->x0 > d->x1)
         return set_error(GD_ERR_INVALID, "gd_conv_taps_bf16: output window outside the grid");
-    if (d->out_ld % 8 || d->out_ld < d->c_out) return set_error(GD_ERR_INVALID, "gd_conv_taps_bf16: out_ld must be >= c_out and a multiple of 8");
+    if (d->out_ld % 8 || d->out_ld < (d->split_out ? 2 : 1) * d->c_store)
+        return set_error(GD_ERR_INVALID, "gd_conv_taps_bf16: out_ld must hold the stored channels and be a multiple of 8");
     const int64_t rows = (int64_t)d->n_images * d->grid_h * d->grid_w;
     if (rows >= ((int64_t)1 << 31) - 65536) return set_error(GD_ERR_INVALID, "gd_conv_taps_bf16: too many pixel rows");
     if ((reinterpret_cast<uintptr_t>(d->in) | reinterpret_cast<uintptr_t>(d->W) | reinterpret_cast<uintptr_t>(d->out)) & 15)
@@ -792,9 +802,10 @@ extern "C" int gd_conv_taps_bf16(const gd_conv_desc* d, void* stream) {
     int rc = check_device();
     if (rc) return rc;
     GemmParams p{};
-    p.M = (int)rows, p.N = d->c_out, p.K = d->n_taps * d->c_in;
+    p.M = (int)rows, p.N = d->c_out, p.K = d->n_taps * d->k_per_tap;
     p.bias = d->bias, p.scale = d->scale, p.shift = d->shift, p.relu = d->relu;
-    p.kb_per_tap = d->c_in / BLOCK_K;
+    p.kb_per_tap = d->k_per_tap / BLOCK_K, p.a_cols = d->in_ld;
+    p.split_out = d->split_out, p.c_store = d->c_store;
     for (int t = 0; t < d->n_taps; ++t) p.tap_shift[t] = d->tap_shift[t];
     p.grid_h = d->grid_h, p.grid_w = d->grid_w;
     p.y0 = d->y0, p.y1 = d->y1, p.x0 = d->x0, p.x1 = d->x1, p.stride = d->stride;
@@ -805,7 +816,7 @@ extern "C" int gd_conv_taps_bf16(const gd_conv_desc* d, void* stream) {
     const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
     const int bn = (d->c_out % 256 == 0 && m_tiles * (d->c_out / 256) >= sm_count()) ? 256
                    : (d->c_out % 128 == 0 && m_tiles * (d->c_out / 128) >= sm_count()) ? 128 : 64;
-    if (bn == 256) return launch_conv<256>(p, d->in, d->c_in, d->W, s);
-    if (bn == 128) return launch_conv<128>(p, d->in, d->c_in, d->W, s);
-    return launch_conv<64>(p, d->in, d->c_in, d->W, s);
+    if (bn == 256) return launch_conv<256>(p, d->in, d->in_ld, d->W, s);
+    if (bn == 128) return launch_conv<128>(p, d->in, d->in_ld, d->W, s);
+    return launch_conv<64>(p, d->in, d->in_ld, d->W, s);
 }

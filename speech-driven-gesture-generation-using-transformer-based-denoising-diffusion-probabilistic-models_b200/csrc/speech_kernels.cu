@@ -18,12 +18,33 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& q, float (&f)[8]) {
     }
 }
 
+// A feature-map row holds `c` channels as one bf16 plane (split = 0) or as two planes [hi(c) | lo(c)], value = hi + lo.
+__device__ __forceinline__ void load_ch8(const __nv_bfloat16* row, int c, int g, int split, float (&f)[8]) {
+    unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(row) + g), f);
+    if (split) {
+        float l[8];
+        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(row + c) + g), l);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += l[j];
+    }
+}
+__device__ __forceinline__ void store_ch8(__nv_bfloat16* row, int c, int g, int split, const float (&v)[8]) {
+    const uint4 hi = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    reinterpret_cast<uint4*>(row)[g] = hi;
+    if (split) {
+        float h[8];
+        unpack_bf16x8(hi, h);
+        reinterpret_cast<uint4*>(row + c)[g] = make_uint4(pack_bf16x2(v[0] - h[0], v[1] - h[1]), pack_bf16x2(v[2] - h[2], v[3] - h[3]),
+                                                          pack_bf16x2(v[4] - h[4], v[5] - h[5]), pack_bf16x2(v[6] - h[6], v[7] - h[7]));
+    }
+}
+
 // ------------------------------------------------------------------------------------------ stem
 // conv1 (1 -> c_real, 3x3, zero padding, bias) + ReLU + folded BatchNorm.  One thread = one pixel x 8 channels.
 __global__ void __launch_bounds__(256) speech_stem_kernel(const float* __restrict__ mel, const float* __restrict__ w,
                                                           const float* __restrict__ bias, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
-                                                          int n_images, int H, int W, int c_real, int c_pad) {
+                                                          int n_images, int H, int W, int c_real, int c_pad, int split) {
     extern __shared__ float s_par[];  // [c_real*9 | c_real | c_real | c_real]
     pdl_launch_dependents();
     pdl_wait();
@@ -42,7 +63,7 @@ __global__ void __launch_bounds__(256) speech_stem_kernel(const float* __restric
     const int img = (int)(pix / ((size_t)H * W));
     const int rem = (int)(pix - (size_t)img * H * W);
     const int y = rem / W, x = rem - y * W;
-    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (g * 8 < c_real) {
         float m[9];
         const float* base = mel + (size_t)img * H * W;
@@ -53,7 +74,6 @@ __global__ void __launch_bounds__(256) speech_stem_kernel(const float* __restric
                 const int yy = y + ky - 1, xx = x + kx - 1;
                 m[ky * 3 + kx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(base + yy * W + xx) : 0.f;
             }
-        float r[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = g * 8 + j;
@@ -65,17 +85,16 @@ __global__ void __launch_bounds__(256) speech_stem_kernel(const float* __restric
             }
             r[j] = acc;
         }
-        o = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
     }
     const size_t orow = (size_t)img * (H + 2) * (W + 2) + (size_t)(y + 1) * (W + 2) + (x + 1);
-    reinterpret_cast<uint4*>(out + orow * c_pad)[g] = o;
+    store_ch8(out + orow * (split ? 2 * c_pad : c_pad), c_pad, g, split, r);
 }
 
 // ------------------------------------------------------------------------------------------ squeeze-excite gate
 // One CTA per image: channel sums over every pixel row of the grid (the border is zero) in a fixed order, then the two
 // tiny Linear layers.  c <= 256.
 __global__ void __launch_bounds__(256) se_gate_kernel(const __nv_bfloat16* __restrict__ y, int grid_px, int interior_px, int c,
-                                                      int c_real, int c_hidden, const float* __restrict__ w1,
+                                                      int split, int c_real, int c_hidden, const float* __restrict__ w1,
                                                       const float* __restrict__ b1, const float* __restrict__ w2,
                                                       const float* __restrict__ b2, float* __restrict__ gate) {
     __shared__ float s_part[256 * 8];
@@ -88,11 +107,12 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const __nv_bfloat16* __res
     const int lanes = 256 / groups;       // pixel rows read concurrently
     const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const uint4* base = reinterpret_cast<const uint4*>(y + (size_t)img * grid_px * c);
+    const int ld = split ? 2 * c : c;
+    const __nv_bfloat16* base = y + (size_t)img * grid_px * ld;
     if (pl < lanes) {
         for (int p = pl; p < grid_px; p += lanes) {
             float f[8];
-            unpack_bf16x8(__ldg(base + (size_t)p * groups + g), f);
+            load_ch8(base + (size_t)p * ld, c, g, split, f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] += f[j];
         }
@@ -118,7 +138,7 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const __nv_bfloat16* __res
         if (threadIdx.x < c_real) {
             float a = b2[threadIdx.x];
             for (int j = 0; j < c_hidden; ++j) a = fmaf(w2[threadIdx.x * c_hidden + j], s_hid[j], a);
-            gv = 1.0f / (1.0f + __expf(-a));
+            gv = 1.0f / (1.0f + expf(-a));
         }
         gate[(size_t)img * c + threadIdx.x] = gv;
     }
@@ -129,10 +149,11 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const __nv_bfloat16* __res
 __global__ void __launch_bounds__(256) se_residual_relu_kernel(const __nv_bfloat16* __restrict__ y,
                                                                const __nv_bfloat16* __restrict__ res,
                                                                const float* __restrict__ gate, __nv_bfloat16* __restrict__ out,
-                                                               int n_images, int grid_h, int grid_w, int c) {
+                                                               int n_images, int grid_h, int grid_w, int c, int split) {
     pdl_launch_dependents();
     pdl_wait();
     const int groups = c >> 3;
+    const int ld = split ? 2 * c : c;
     const int H = grid_h - 2, W = grid_w - 2;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t pix = idx / groups;
@@ -143,26 +164,26 @@ __global__ void __launch_bounds__(256) se_residual_relu_kernel(const __nv_bfloat
     const int py = rem / W, px = rem - py * W;
     const size_t row = (size_t)img * grid_h * grid_w + (size_t)(py + 1) * grid_w + (px + 1);
     float a[8], r[8];
-    unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(y + row * c) + g), a);
-    unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(res + row * c) + g), r);
+    load_ch8(y + row * ld, c, g, split, a);
+    load_ch8(res + row * ld, c, g, split, r);
     const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + (size_t)img * c) + 2 * g);
     const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + (size_t)img * c) + 2 * g + 1);
     const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = fmaxf(fmaf(gv[j], a[j], r[j]), 0.f);
-    reinterpret_cast<uint4*>(out + row * c)[g] =
-        make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    store_ch8(out + row * ld, c, g, split, o);
 }
 
 // ------------------------------------------------------------------------------------------ pixel shuffle
-// out[img, y*r+i, x*r+j, ch] = in[img, y+1, x+1, ch*r*r + i*r + j]; ch >= c_in/r^2 written as 0.
+// out[img, y*r+i, x*r+j, ch] = in[img, y+1, x+1, ch*r*r + i*r + j]; ch >= c_in/r^2 written as 0.  Split rows: both planes.
 __global__ void __launch_bounds__(256) pixel_shuffle_rows_kernel(const __nv_bfloat16* __restrict__ in,
                                                                  __nv_bfloat16* __restrict__ out, int n_images, int H, int W,
-                                                                 int c_in, int r, int c_out_pad) {
+                                                                 int c_in, int r, int c_out_pad, int split) {
     pdl_launch_dependents();
     pdl_wait();
     const int groups = c_out_pad >> 3;
+    const int planes = split ? 2 : 1;
     const int Ho = H * r, Wo = W * r, c_real = c_in / (r * r);
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t pix = idx / groups;
@@ -172,18 +193,21 @@ __global__ void __launch_bounds__(256) pixel_shuffle_rows_kernel(const __nv_bflo
     const int rem = (int)(pix - (size_t)img * Ho * Wo);
     const int oy = rem / Wo, ox = rem - oy * Wo;
     const int y = oy / r, i = oy - y * r, x = ox / r, j = ox - x * r;
-    const unsigned short* src = reinterpret_cast<const unsigned short*>(in) +
-                                ((size_t)img * (H + 2) * (W + 2) + (size_t)(y + 1) * (W + 2) + (x + 1)) * c_in + i * r + j;
-    unsigned short v[8];
+    for (int pl = 0; pl < planes; ++pl) {
+        const unsigned short* src = reinterpret_cast<const unsigned short*>(in) +
+                                    ((size_t)img * (H + 2) * (W + 2) + (size_t)(y + 1) * (W + 2) + (x + 1)) * (planes * c_in) +
+                                    pl * c_in + i * r + j;
+        unsigned short v[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int ch = g * 8 + k;
-        v[k] = ch < c_real ? __ldg(src + ch * r * r) : (unsigned short)0;
+        for (int k = 0; k < 8; ++k) {
+            const int ch = g * 8 + k;
+            v[k] = ch < c_real ? __ldg(src + ch * r * r) : (unsigned short)0;
+        }
+        uint4 o;
+        o.x = v[0] | ((uint32_t)v[1] << 16), o.y = v[2] | ((uint32_t)v[3] << 16);
+        o.z = v[4] | ((uint32_t)v[5] << 16), o.w = v[6] | ((uint32_t)v[7] << 16);
+        reinterpret_cast<uint4*>(out + pix * (planes * c_out_pad) + pl * c_out_pad)[g] = o;
     }
-    uint4 o;
-    o.x = v[0] | ((uint32_t)v[1] << 16), o.y = v[2] | ((uint32_t)v[3] << 16);
-    o.z = v[4] | ((uint32_t)v[5] << 16), o.w = v[6] | ((uint32_t)v[7] << 16);
-    reinterpret_cast<uint4*>(out + pix * c_out_pad)[g] = o;
 }
 
 }  // namespace gd
@@ -192,56 +216,56 @@ using namespace gd;
 
 extern "C" int gd_speech_stem(const float* mel, const float* w, const float* bias, const float* scale, const float* shift,
                               void* out_bf16, int32_t n_images, int32_t H, int32_t W, int32_t c_real, int32_t c_pad,
-                              void* stream) {
+                              int32_t split, void* stream) {
     if (!mel || !w || !bias || !scale || !shift || !out_bf16) return set_error(GD_ERR_INVALID, "gd_speech_stem: null pointer");
     if (n_images <= 0 || H <= 0 || W <= 0 || c_real <= 0 || c_real > c_pad || c_pad % 8 || c_real > 256)
         return set_error(GD_ERR_INVALID, "gd_speech_stem: bad shape");
     const size_t total = (size_t)n_images * H * W * (c_pad / 8);
     GD_CUDA_CHECK(launch_k(speech_stem_kernel, grid_for(total, 256), 256, (size_t)c_real * 12 * sizeof(float),
                            reinterpret_cast<cudaStream_t>(stream), 1, mel, w, bias, scale, shift,
-                           reinterpret_cast<__nv_bfloat16*>(out_bf16), n_images, H, W, c_real, c_pad));
+                           reinterpret_cast<__nv_bfloat16*>(out_bf16), n_images, H, W, c_real, c_pad, split));
     count_launch();
     GD_CUDA_CHECK(cudaGetLastError());
     return GD_OK;
 }
 
-extern "C" int gd_se_gate(const void* y_bf16, int32_t n_images, int32_t grid_h, int32_t grid_w, int32_t c, int32_t c_real,
-                          int32_t c_hidden, const float* w1, const float* b1, const float* w2, const float* b2, float* gate,
+extern "C" int gd_se_gate(const void* y_bf16, int32_t n_images, int32_t grid_h, int32_t grid_w, int32_t c, int32_t split,
+                          int32_t c_real, int32_t c_hidden, const float* w1, const float* b1, const float* w2, const float* b2, float* gate,
                           void* stream) {
     if (!y_bf16 || !w1 || !b1 || !w2 || !b2 || !gate) return set_error(GD_ERR_INVALID, "gd_se_gate: null pointer");
-    if (n_images <= 0 || grid_h < 3 || grid_w < 3 || c < 64 || c > 256 || c % 64 || c_real <= 0 || c_real > c ||
+    if (n_images <= 0 || grid_h < 3 || grid_w < 3 || c < 32 || c > 256 || (c & (c - 1)) || c_real <= 0 || c_real > c ||
         c_hidden <= 0 || c_hidden > 32)
-        return set_error(GD_ERR_INVALID, "gd_se_gate: bad shape (c in {64,128,192,256}, c_hidden <= 32)");
+        return set_error(GD_ERR_INVALID, "gd_se_gate: bad shape (c in {32,64,128,256}, c_hidden <= 32)");
     GD_CUDA_CHECK(launch_k(se_gate_kernel, n_images, 256, 0, reinterpret_cast<cudaStream_t>(stream), 1,
                            reinterpret_cast<const __nv_bfloat16*>(y_bf16), grid_h * grid_w, (grid_h - 2) * (grid_w - 2), c,
-                           c_real, c_hidden, w1, b1, w2, b2, gate));
+                           split, c_real, c_hidden, w1, b1, w2, b2, gate));
     count_launch();
     GD_CUDA_CHECK(cudaGetLastError());
     return GD_OK;
 }
 
 extern "C" int gd_se_residual_relu(const void* y_bf16, const void* residual_bf16, const float* gate, void* out_bf16,
-                                   int32_t n_images, int32_t grid_h, int32_t grid_w, int32_t c, void* stream) {
+                                   int32_t n_images, int32_t grid_h, int32_t grid_w, int32_t c, int32_t split, void* stream) {
     if (!y_bf16 || !residual_bf16 || !gate || !out_bf16) return set_error(GD_ERR_INVALID, "gd_se_residual_relu: null pointer");
     if (n_images <= 0 || grid_h < 3 || grid_w < 3 || c <= 0 || c % 8) return set_error(GD_ERR_INVALID, "gd_se_residual_relu: bad shape");
     const size_t total = (size_t)n_images * (grid_h - 2) * (grid_w - 2) * (c / 8);
     GD_CUDA_CHECK(launch_k(se_residual_relu_kernel, grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), 1,
                            reinterpret_cast<const __nv_bfloat16*>(y_bf16), reinterpret_cast<const __nv_bfloat16*>(residual_bf16),
-                           gate, reinterpret_cast<__nv_bfloat16*>(out_bf16), n_images, grid_h, grid_w, c));
+                           gate, reinterpret_cast<__nv_bfloat16*>(out_bf16), n_images, grid_h, grid_w, c, split));
     count_launch();
     GD_CUDA_CHECK(cudaGetLastError());
     return GD_OK;
 }
 
 extern "C" int gd_pixel_shuffle_rows(const void* in_bf16, void* out_bf16, int32_t n_images, int32_t H, int32_t W,
-                                     int32_t c_in, int32_t r, int32_t c_out_pad, void* stream) {
+                                     int32_t c_in, int32_t r, int32_t c_out_pad, int32_t split, void* stream) {
     if (!in_bf16 || !out_bf16) return set_error(GD_ERR_INVALID, "gd_pixel_shuffle_rows: null pointer");
     if (n_images <= 0 || H <= 0 || W <= 0 || r < 1 || c_in % (r * r) || c_out_pad % 8 || c_in / (r * r) > c_out_pad)
         return set_error(GD_ERR_INVALID, "gd_pixel_shuffle_rows: bad shape");
     const size_t total = (size_t)n_images * H * r * W * r * (c_out_pad / 8);
     GD_CUDA_CHECK(launch_k(pixel_shuffle_rows_kernel, grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), 1,
                            reinterpret_cast<const __nv_bfloat16*>(in_bf16), reinterpret_cast<__nv_bfloat16*>(out_bf16), n_images,
-                           H, W, c_in, r, c_out_pad));
+                           H, W, c_in, r, c_out_pad, split));
     count_launch();
     GD_CUDA_CHECK(cudaGetLastError());
     return GD_OK;

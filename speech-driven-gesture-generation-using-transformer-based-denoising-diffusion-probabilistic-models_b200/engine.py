@@ -216,11 +216,12 @@ class SamplingChain:
         # its kernels sum to less - the stand-alone LayerNorm overlaps with its neighbours, the cluster kernel does not.
         self.fuse_ln = bool(int(env("GD_FUSE_LN", int(fuse_ln))))
         self.encoder_chunk = getattr(model, "encoder_chunk", 16)
-        # once-per-clip speech encoder: "native" = ResNetSE-34 on our tensor-core convolutions (bf16 operands, fp32
-        # accumulation), "torch" = the fp32 nn.Module through cuDNN (always used by the fp32-activation parity path)
+        # once-per-clip speech encoder: "native" = ResNetSE-34 on our tensor-core convolutions in split precision (bf16x3:
+        # fp32-class products), "native-bf16" = the same with plain bf16 feature maps (faster, ~1e-2 feature error that a
+        # random-weight ResNet amplifies), "torch" = the fp32 nn.Module through cuDNN (the fp32-activation parity path)
         self.speech_impl = "torch" if self.f32act else env("GD_SPEECH", getattr(model, "speech_impl", "native"))
-        if self.speech_impl not in ("native", "torch"):
-            raise ValueError(f"speech_impl must be 'native' or 'torch', got {self.speech_impl!r}")
+        if self.speech_impl not in ("native", "native-bf16", "torch"):
+            raise ValueError(f"speech_impl must be 'native', 'native-bf16' or 'torch', got {self.speech_impl!r}")
         self.native_encoder_chunk = getattr(model, "native_encoder_chunk", 64)
         self.graph = None
         self._plan_key = None
@@ -241,12 +242,14 @@ class SamplingChain:
         prev = th.backends.cudnn.allow_tf32, th.backends.cuda.matmul.allow_tf32
         th.backends.cudnn.allow_tf32 = th.backends.cuda.matmul.allow_tf32 = False  # reference math is fp32
         try:
-            if self.speech_impl == "native":  # ResNetSE-34 trunk + heads on our kernels (speech_native.py)
-                key = (self.model.weights_version, str(self.device), self.native_encoder_chunk)
+            if self.speech_impl != "torch":  # ResNetSE-34 trunk + heads on our kernels (speech_native.py)
+                precision = "bf16" if self.speech_impl == "native-bf16" else "bf16x3"
+                key = (self.model.weights_version, str(self.device), self.native_encoder_chunk, precision)
                 cached = getattr(self.model, "_native_speech", None)  # packed once per (weights, device), shared by chains
                 if cached is None or cached[0] != key:
                     from .speech_native import NativeSpeechEncoder
-                    cached = (key, NativeSpeechEncoder(enc, self.L, self.device, chunk=self.native_encoder_chunk))
+                    cached = (key, NativeSpeechEncoder(enc, self.L, self.device, chunk=self.native_encoder_chunk,
+                                                       precision=precision))
                     self.model._native_speech = cached
                 return cached[1](wav)
             # fixed-size micro-batches (last one zero-padded): cuDNN then runs the same algorithm whatever the batch

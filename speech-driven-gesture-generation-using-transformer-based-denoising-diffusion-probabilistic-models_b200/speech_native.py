@@ -5,15 +5,19 @@ kernels of csrc/speech_kernels.cu.  The module packs the weights of a `modules.S
 parameter holder) once, owns the feature-map workspace and turns wav (N, T_wav) into the three (N, T_k, d_model)
 feature sequences.
 
-Layout: every feature map is channel-last bf16 "pixel rows" on a zero-bordered grid (include/gd_b200.h); layers narrower
-than 64 channels are zero-padded to 64 (BLOCK_K of the GEMM).  BatchNorm (eval) is folded to a per-channel scale/shift in
-the convolution epilogue; the last Linear of each head (`fc_low/mid/high`) and the shared `wav_proj_layer` are two
-consecutive affine maps and are multiplied together on the host (fp32) into one [d_model, H_k*64] GEMM per head.
+Layout: every feature map is channel-last bf16 "pixel rows" on a zero-bordered grid (include/gd_b200.h).  BatchNorm (eval)
+is folded to a per-channel scale/shift in the convolution epilogue; the last Linear of each head (`fc_low/mid/high`) and
+the shared `wav_proj_layer` are two consecutive affine maps and are multiplied together on the host (fp64) into one
+GEMM per head.
 
-Arithmetic: bf16 operands, fp32 accumulation, bf16 feature maps - the same contract as the denoiser's GEMMs.  Every kernel
-treats pixel rows independently and reduces in a fixed order, so a clip's features do not depend on its batch.  The
-mel front end (pre-emphasis, STFT, mel filterbank, InstanceNorm1d) is evaluated by `SpeechEncoder.wav2spec` in fixed
-micro-batches.
+Arithmetic.  A 34-convolution random-weight ResNet amplifies rounding noise: with plain bf16 feature maps the "boosted"
+parity weights give 2-6 % feature error and 4-9 % eps error (measured), far outside the 2e-2 budget.  The default
+precision is therefore "bf16x3": feature maps are stored as two bf16 planes [hi | lo] (value = hi + lo), weights are split
+the same way on the host, and each convolution accumulates hi*Whi + lo*Whi + hi*Wlo in fp32 on the tensor cores -
+fp32-class products at a third of the bf16 rate.  "bf16" (one plane, narrow layers zero-padded to 64 channels) is kept
+as the fast option.  Every kernel treats pixel rows independently and reduces in a fixed order, so a clip's features do
+not depend on its batch.  The mel front end (pre-emphasis, STFT, mel filterbank, InstanceNorm1d) is evaluated by
+`SpeechEncoder.wav2spec` in fixed micro-batches.
 """
 import ctypes as C
 
@@ -49,20 +53,36 @@ def _pad_vec(v, c_pad):
     return out
 
 
-def _pack_conv(weight, ci_pad, co_pad):
-    """(Co, Ci, kh, kw) -> bf16 [co_pad, kh*kw*ci_pad], taps (ky, kx) row-major along K, channels innermost."""
+def _pack_conv(weight, c_in, co_pad, split):
+    """(Co, Ci, kh, kw) -> bf16 [co_pad, kh*kw*k_per_tap]: taps (ky, kx) row-major along K, then the K walk of one tap over an
+    input row of `c_in` stored channels.  Plain rows: k = channel.  Split rows [hi(c_in) | lo(c_in)]: the walk wraps around
+    the row; the first pass multiplies both planes by Whi, the second pass multiplies the hi plane by Wlo (bf16x3)."""
     co, ci, kh, kw = weight.shape
-    w = th.zeros(co_pad, kh * kw, ci_pad, dtype=th.float32, device=weight.device)
-    w[:co, :, :ci] = weight.float().permute(0, 2, 3, 1).reshape(co, kh * kw, ci)
-    return w.reshape(co_pad, kh * kw * ci_pad).to(th.bfloat16).contiguous()
+    taps = kh * kw
+    w = th.zeros(co_pad, taps, c_in, dtype=th.float32, device=weight.device)
+    w[:co, :, :ci] = weight.float().permute(0, 2, 3, 1).reshape(co, taps, ci)
+    if not split:
+        return w.reshape(co_pad, taps * c_in).to(th.bfloat16).contiguous(), c_in
+    whi = w.to(th.bfloat16).float()
+    wlo = (w - whi).to(th.bfloat16).float()
+    in_ld, k_per_tap = 2 * c_in, _pad_to(3 * c_in)
+    k = th.arange(k_per_tap, device=weight.device)
+    col, second = k % in_ld, k >= in_ld
+    ch, lo_plane = col % c_in, col >= c_in
+    out = th.where(second[None, None, :], th.where(lo_plane[None, None, :], wlo.new_zeros(()), wlo[:, :, ch]), whi[:, :, ch])
+    return out.reshape(co_pad, taps * k_per_tap).to(th.bfloat16).contiguous(), k_per_tap
 
 
 class _Conv:
-    """Packed parameters of one Conv2d [+ReLU] + BatchNorm2d."""
+    """Packed parameters of one Conv2d [+ReLU] + BatchNorm2d reading a feature map of `c_in` stored channels."""
 
-    def __init__(self, conv, bn, relu, ci_pad):
-        self.c_in, self.c_out = ci_pad, _pad_to(conv.out_channels)
-        self.w = _pack_conv(conv.weight.detach(), ci_pad, self.c_out)
+    def __init__(self, conv, bn, relu, c_in, split):
+        self.split = split
+        self.c_out = _pad_to(conv.out_channels)                       # GEMM N
+        self.c_store = _pad_to(conv.out_channels, 32) if split else self.c_out
+        self.in_ld = 2 * c_in if split else c_in
+        self.out_ld = 2 * self.c_store if split else self.c_store
+        self.w, self.k_per_tap = _pack_conv(conv.weight.detach(), c_in, self.c_out, split)
         self.bias = _pad_vec(conv.bias.detach() if conv.bias is not None else None, self.c_out)
         self.scale, self.shift = _fold_bn(bn, self.c_out)
         self.relu = int(relu)
@@ -71,11 +91,11 @@ class _Conv:
 
 
 class _Block:
-    def __init__(self, blk, ci_pad):
-        self.conv1 = _Conv(blk.conv1, blk.bn1, True, ci_pad)
-        c = self.conv1.c_out
-        self.conv2 = _Conv(blk.conv2, blk.bn2, False, c)
-        self.down = None if blk.downsample is None else _Conv(blk.downsample[0], blk.downsample[1], False, ci_pad)
+    def __init__(self, blk, c_in, split):
+        self.conv1 = _Conv(blk.conv1, blk.bn1, True, c_in, split)
+        c = self.conv1.c_store
+        self.conv2 = _Conv(blk.conv2, blk.bn2, False, c, split)
+        self.down = None if blk.downsample is None else _Conv(blk.downsample[0], blk.downsample[1], False, c_in, split)
         fc1, fc2 = blk.se.fc[0], blk.se.fc[2]
         self.c, self.c_real, self.c_hidden = c, fc2.out_features, fc1.out_features
         self.se = [t.detach().float().contiguous() for t in (fc1.weight, fc1.bias, fc2.weight, fc2.bias)]
@@ -84,16 +104,18 @@ class _Block:
 class _Head:
     """conv_k + ReLU + bn_k, then fc_k and wav_proj_layer merged into one affine map over the [y][c] features of a frame."""
 
-    def __init__(self, conv, bn, fc, proj, shuffle, ci_pad, h_out):
-        self.conv = _Conv(conv, bn, True, ci_pad)
+    def __init__(self, conv, bn, fc, proj, shuffle, c_in, h_out, split):
+        self.conv = _Conv(conv, bn, True, c_in, split)
         self.shuffle, self.h_out = shuffle, h_out
-        cr = conv.out_channels
+        cr, cs = conv.out_channels, self.conv.c_store
         assert fc.in_features == cr * h_out, "pyramid head: fc width does not match the 128-bin mel image"
         wfc = fc.weight.detach().double().reshape(fc.out_features, cr, h_out).permute(0, 2, 1)  # [o, y, c]
-        wfc_p = th.zeros(fc.out_features, h_out, self.conv.c_out, dtype=th.float64, device=wfc.device)
+        wfc_p = th.zeros(fc.out_features, h_out, self.conv.out_ld, dtype=th.float64, device=wfc.device)
         wfc_p[:, :, :cr] = wfc
+        if split:
+            wfc_p[:, :, cs:cs + cr] = wfc  # the lo plane of the features meets the same weights
         wp = proj.weight.detach().double()
-        self.w = (wp @ wfc_p.reshape(fc.out_features, -1)).to(th.bfloat16).contiguous()      # [d, h_out*c_pad]
+        self.w = (wp @ wfc_p.reshape(fc.out_features, -1)).to(th.bfloat16).contiguous()      # [d, h_out*row width]
         self.b = (wp @ fc.bias.detach().double() + proj.bias.detach().double()).float().contiguous()
 
 
@@ -102,24 +124,29 @@ class NativeSpeechEncoder:
 
     MEL_CHUNK = 16  # the mel front end runs in fixed micro-batches (library FFT / matmul pick algorithms per batch size)
 
-    def __init__(self, enc, launcher, device, chunk=64):
+    def __init__(self, enc, launcher, device, chunk=64, precision="bf16x3"):
+        if precision not in ("bf16x3", "bf16"):
+            raise ValueError(f"speech precision must be 'bf16x3' or 'bf16', got {precision!r}")
         self.enc, self.L, self.lib, self.dev, self.chunk = enc, launcher, launcher.lib, device, chunk
+        self.split = split = int(precision == "bf16x3")
         r = enc.wav_encoder.feat_extractor
         self.d = enc.wav_proj_layer.out_features
         self.stem_c = r.conv1.out_channels
+        self.stem_store = _pad_to(self.stem_c, 32 if split else PAD)
         self.stem = [r.conv1.weight.detach().float().reshape(self.stem_c, 9).contiguous(), r.conv1.bias.detach().float().contiguous(),
                      *[t[:self.stem_c].contiguous() for t in _fold_bn(r.bn1, _pad_to(self.stem_c))]]
-        self.stages, c = [], _pad_to(self.stem_c)
+        self.stages, c = [], self.stem_store
         for layer in (r.layer1, r.layer2, r.layer3, r.layer4):
             blocks = []
             for blk in layer:
-                blocks.append(_Block(blk, c))
+                blocks.append(_Block(blk, c, split))
                 c = blocks[-1].c
             self.stages.append(blocks)
         proj = enc.wav_proj_layer
-        self.heads = [_Head(r.conv_low, r.bn_low, r.fc_low, proj, 1, self.stages[1][0].c, 63),
-                      _Head(r.conv_mid, r.bn_mid, r.fc_mid, proj, 2, PAD, 62),
-                      _Head(r.conv_high, r.bn_high, r.fc_high, proj, 4, PAD, 62)]
+        self.shuffle_c = 32 if split else PAD  # stored channels of the pixel-shuffled maps (32 / 16 real)
+        self.heads = [_Head(r.conv_low, r.bn_low, r.fc_low, proj, 1, self.stages[1][0].c, 63, split),
+                      _Head(r.conv_mid, r.bn_mid, r.fc_mid, proj, 2, self.shuffle_c, 62, split),
+                      _Head(r.conv_high, r.bn_high, r.fc_high, proj, 4, self.shuffle_c, 62, split)]
         self._ws = {}
 
     # ------------------------------------------------------------------ workspace
@@ -130,20 +157,22 @@ class NativeSpeechEncoder:
             return ws
         self._ws.clear()  # one geometry at a time
         z = lambda rows, c, dt=th.bfloat16: th.zeros(rows, c, device=self.dev, dtype=dt)  # noqa: E731
+        planes = 2 if self.split else 1
         H, W, stages = 128, F, []
         for s, blocks in enumerate(self.stages):
             if s > 0:
                 H, W = (H - 1) // 2 + 1, (W - 1) // 2 + 1
             c, rows = blocks[0].c, n * (H + 2) * (W + 2)
-            stages.append({"H": H, "W": W, "c": c, "x": [z(rows, c), z(rows, c)], "y1": z(rows, c), "y2": z(rows, c),
-                           "r": z(rows, c) if blocks[0].down is not None else None, "gate": z(n, c, th.float32)})
+            ld = planes * c
+            stages.append({"H": H, "W": W, "c": c, "x": [z(rows, ld), z(rows, ld)], "y1": z(rows, ld), "y2": z(rows, ld),
+                           "r": z(rows, ld) if blocks[0].down is not None else None, "gate": z(n, c, th.float32)})
         heads = []
         for k, hd in enumerate(self.heads):
             st = stages[k + 1]
             gh, gw = st["H"] * hd.shuffle, st["W"] * hd.shuffle
             w_out = gw - 1 if k == 0 else gw - 2
-            heads.append({"g": None if hd.shuffle == 1 else z(n * gh * gw, PAD), "gh": gh, "gw": gw, "T": w_out,
-                          "feat": z(n * w_out, hd.h_out * hd.conv.c_out), "z": z(n * w_out, self.d, th.float32)})
+            heads.append({"g": None if hd.shuffle == 1 else z(n * gh * gw, planes * self.shuffle_c), "gh": gh, "gw": gw,
+                          "T": w_out, "feat": z(n * w_out, hd.h_out * hd.conv.out_ld), "z": z(n * w_out, self.d, th.float32)})
         ws = self._ws[F] = {"cap": n, "stages": stages, "heads": heads}
         return ws
 
@@ -151,14 +180,15 @@ class NativeSpeechEncoder:
     def _conv(self, cv, src, n, gh, gw, taps, window, stride, dst, out_strides):
         d = gd.ConvDesc()
         d.inp, d.W, d.n_images, d.grid_h, d.grid_w = _p(src), _p(cv.w), n, gh, gw
-        d.c_in, d.c_out, d.n_taps = cv.c_in, cv.c_out, len(taps)
+        d.in_ld, d.k_per_tap, d.c_out, d.n_taps = cv.in_ld, cv.k_per_tap, cv.c_out, len(taps)
         for i, t in enumerate(taps):
             d.tap_shift[i] = t
         d.bias, d.scale, d.shift, d.relu = _p(cv.bias), _p(cv.scale), _p(cv.shift), cv.relu
         d.y0, d.y1, d.x0, d.x1 = window
         d.stride = stride
-        d.out, d.out_ld = _p(dst), cv.c_out
+        d.out, d.out_ld = _p(dst), cv.out_ld
         d.out_img_stride, d.out_y_stride, d.out_x_stride, d.out_offset = out_strides
+        d.c_store, d.split_out = cv.c_store, cv.split
         gd.check(self.lib.gd_conv_taps_bf16(C.byref(d), self.L.stream()), "gd_conv_taps_bf16")
 
     def _same_conv(self, cv, src, n, src_hw, dst, dst_hw):
@@ -175,7 +205,9 @@ class NativeSpeechEncoder:
         st = ws["stages"]
         x = st[0]["x"][0]
         w, b, sc, sh = self.stem
-        gd.check(lib.gd_speech_stem(_p(mel), _p(w), _p(b), _p(sc), _p(sh), _p(x), n, H, F, self.stem_c, st[0]["c"], s), "gd_speech_stem")
+        sp = self.split
+        gd.check(lib.gd_speech_stem(_p(mel), _p(w), _p(b), _p(sc), _p(sh), _p(x), n, H, F, self.stem_c, self.stem_store, sp, s),
+                 "gd_speech_stem")
         prev_hw = (H, F)
         for si, blocks in enumerate(self.stages):
             g = st[si]
@@ -188,10 +220,10 @@ class NativeSpeechEncoder:
                 if blk.down is not None:
                     self._same_conv(blk.down, x, n, in_hw, g["r"], hw)
                     res = g["r"]
-                gd.check(lib.gd_se_gate(_p(g["y2"]), n, hw[0] + 2, hw[1] + 2, c, blk.c_real, blk.c_hidden,
+                gd.check(lib.gd_se_gate(_p(g["y2"]), n, hw[0] + 2, hw[1] + 2, c, sp, blk.c_real, blk.c_hidden,
                                         *[_p(t) for t in blk.se], _p(g["gate"]), s), "gd_se_gate")
                 out = g["x"][1] if x is g["x"][0] else g["x"][0]
-                gd.check(lib.gd_se_residual_relu(_p(g["y2"]), _p(res), _p(g["gate"]), _p(out), n, hw[0] + 2, hw[1] + 2, c, s),
+                gd.check(lib.gd_se_residual_relu(_p(g["y2"]), _p(res), _p(g["gate"]), _p(out), n, hw[0] + 2, hw[1] + 2, c, sp, s),
                          "gd_se_residual_relu")
                 x = out
             g["out"] = x
@@ -205,11 +237,11 @@ class NativeSpeechEncoder:
                 self._conv(hd.conv, g["out"], n, g["H"] + 2, gwb, [0, 1, gwb, gwb + 1], (1, g["H"] - 1, 1, g["W"] - 1), 1,
                            h["feat"], (T * hd.h_out, 1, hd.h_out, 0))
             else:                 # pixel shuffle to an unbordered grid, then a 3x3 valid convolution
-                gd.check(lib.gd_pixel_shuffle_rows(_p(g["out"]), _p(h["g"]), n, g["H"], g["W"], g["c"], hd.shuffle, PAD, s),
+                gd.check(lib.gd_pixel_shuffle_rows(_p(g["out"]), _p(h["g"]), n, g["H"], g["W"], g["c"], hd.shuffle, self.shuffle_c, sp, s),
                          "gd_pixel_shuffle_rows")
                 taps = [(ky - 1) * gw + (kx - 1) for ky in range(3) for kx in range(3)]
                 self._conv(hd.conv, h["g"], n, gh, gw, taps, (1, gh - 2, 1, gw - 2), 1, h["feat"], (T * hd.h_out, 1, hd.h_out, 0))
-            K = hd.h_out * hd.conv.c_out
+            K = hd.h_out * hd.conv.out_ld
             self.L.linear(h["feat"], hd.w, n * T, self.d, K, bias=hd.b, out_f32=h["z"])()
             outs.append(h["z"][:n * T].view(n, T, self.d))
         return outs

@@ -11,18 +11,34 @@ def bf16_round(t):
     return t.to(th.bfloat16).float()
 
 
-def conv_taps_ref(inp, W, n_images, grid_h, grid_w, taps, bias, scale, shift, relu, window, stride, out, out_strides):
-    """gd_conv_taps_bf16 on tensors: inp [rows, c_in], W [c_out, n_taps*c_in], out [*, c_out] modified in place."""
-    rows, c_in = n_images * grid_h * grid_w, inp.shape[1]
+def join(t, c, split):
+    """value of a feature-map row tensor [rows, c] or [rows, hi(c) | lo(c)] as fp32 [rows, c]."""
+    return t[:, :c].float() + t[:, c:2 * c].float() if split else t[:, :c].float()
+
+
+def put(out, index, v, c, split):
+    """store fp32 values [*, c] into rows `index` of a plain / split feature map (bf16 emulated by the tensor dtype
+    or, for fp32 stand-ins on CPU, by rounding)."""
+    hi = v.to(th.bfloat16)
+    out[index, :c] = hi.to(out.dtype)
+    if split:
+        out[index, c:2 * c] = (v - hi.float()).to(th.bfloat16).to(out.dtype)
+
+
+def conv_taps_ref(inp, W, n_images, grid_h, grid_w, taps, k_per_tap, bias, scale, shift, relu, window, stride, out, out_strides,
+                  c_store, split_out):
+    """gd_conv_taps_bf16 on tensors: inp [rows, in_ld], W [c_out, n_taps*k_per_tap], out [*, out_ld] modified in place."""
+    rows, in_ld = n_images * grid_h * grid_w, inp.shape[1]
     A = inp[:rows].float()
     Wf = W.float()
+    walk = th.arange(k_per_tap, device=inp.device) % in_ld
     acc = th.zeros(rows, W.shape[0], dtype=th.float32, device=inp.device)
     for t, sh in enumerate(taps):
         shifted = th.zeros_like(A)
         lo, hi = max(0, -sh), min(rows, rows - sh)
         if hi > lo:
             shifted[lo:hi] = A[lo + sh:hi + sh]
-        acc += shifted @ Wf[:, t * c_in:(t + 1) * c_in].T
+        acc += shifted[:, walk] @ Wf[:, t * k_per_tap:(t + 1) * k_per_tap].T
     if bias is not None:
         acc = acc + bias
     if relu:
@@ -35,25 +51,25 @@ def conv_taps_ref(inp, W, n_images, grid_h, grid_w, taps, bias, scale, shift, re
     keep = (y >= y0) & (y <= y1) & (x >= x0) & (x <= x1) & ((y - y0) % stride == 0) & ((x - x0) % stride == 0)
     si, sy, sx, off = out_strides
     orow = img * si + ((y - y0) // stride) * sy + ((x - x0) // stride) * sx + off
-    out[orow[keep]] = acc[keep].to(out.dtype)
+    put(out, orow[keep], acc[keep][:, :c_store], c_store, split_out)
     return out
 
 
-def stem_ref(mel, w, bias, scale, shift, out, c_pad):
-    """gd_speech_stem: mel (n, H, W) fp32 -> bordered channel-last rows [n*(H+2)*(W+2), c_pad]."""
+def stem_ref(mel, w, bias, scale, shift, out, c_pad, split=0):
+    """gd_speech_stem: mel (n, H, W) fp32 -> bordered channel-last rows [n*(H+2)*(W+2), c_pad (x2 if split)]."""
     n, H, W = mel.shape
     c = w.shape[0]
     y = th.nn.functional.conv2d(mel[:, None], w.view(c, 1, 3, 3), bias, padding=1).clamp_min(0)
     y = y * scale[None, :, None, None] + shift[None, :, None, None]
-    grid = out[:n * (H + 2) * (W + 2)].view(n, H + 2, W + 2, c_pad)
-    grid[:, 1:H + 1, 1:W + 1, :c] = y.permute(0, 2, 3, 1).to(out.dtype)
-    grid[:, 1:H + 1, 1:W + 1, c:] = 0
+    v = th.zeros(n, H, W, c_pad, device=mel.device)
+    v[..., :c] = y.permute(0, 2, 3, 1)
+    idx = th.arange(n * (H + 2) * (W + 2), device=mel.device).view(n, H + 2, W + 2)[:, 1:-1, 1:-1].reshape(-1)
+    put(out, idx, v.reshape(-1, c_pad), c_pad, split)
     return out
 
 
-def se_gate_ref(y, n_images, grid_h, grid_w, c_real, w1, b1, w2, b2, gate):
-    c = y.shape[1]
-    g = y[:n_images * grid_h * grid_w].float().view(n_images, grid_h * grid_w, c)
+def se_gate_ref(y, n_images, grid_h, grid_w, c, split, c_real, w1, b1, w2, b2, gate):
+    g = join(y[:n_images * grid_h * grid_w], c, split).view(n_images, grid_h * grid_w, c)
     mean = g.sum(dim=1)[:, :c_real] / ((grid_h - 2) * (grid_w - 2))
     a = th.sigmoid(th.relu(mean @ w1.T + b1) @ w2.T + b2)
     gate[:n_images] = 0
@@ -61,22 +77,23 @@ def se_gate_ref(y, n_images, grid_h, grid_w, c_real, w1, b1, w2, b2, gate):
     return gate
 
 
-def se_residual_relu_ref(y, res, gate, out, n_images, grid_h, grid_w):
-    c = y.shape[1]
+def se_residual_relu_ref(y, res, gate, out, n_images, grid_h, grid_w, c, split=0):
     rows = n_images * grid_h * grid_w
-    v = lambda t: t[:rows].view(n_images, grid_h, grid_w, c)  # noqa: E731
-    o = th.relu(gate[:n_images, None, None, :] * v(y).float() + v(res).float())
-    v(out)[:, 1:-1, 1:-1] = o[:, 1:-1, 1:-1].to(out.dtype)
+    v = lambda t: join(t[:rows], c, split).view(n_images, grid_h, grid_w, c)  # noqa: E731
+    o = th.relu(gate[:n_images, None, None, :c] * v(y) + v(res))
+    idx = th.arange(rows, device=y.device).view(n_images, grid_h, grid_w)[:, 1:-1, 1:-1].reshape(-1)
+    put(out, idx, o[:, 1:-1, 1:-1].reshape(-1, c), c, split)
     return out
 
 
-def pixel_shuffle_ref(inp, out, n_images, H, W, r, c_out_pad):
-    c_in = inp.shape[1]
-    feat = inp[:n_images * (H + 2) * (W + 2)].view(n_images, H + 2, W + 2, c_in)[:, 1:-1, 1:-1].permute(0, 3, 1, 2)
-    sh = th.nn.functional.pixel_shuffle(feat.float(), r)  # (n, c_in/r^2, H*r, W*r)
-    o = out[:n_images * H * r * W * r].view(n_images, H * r, W * r, c_out_pad)
+def pixel_shuffle_ref(inp, out, n_images, H, W, c_in, r, c_out_pad, split=0):
+    o = out[:n_images * H * r * W * r]
     o.zero_()
-    o[..., :sh.shape[1]] = sh.permute(0, 2, 3, 1).to(out.dtype)
+    for pl in range(2 if split else 1):
+        plane = inp[:n_images * (H + 2) * (W + 2), pl * c_in:(pl + 1) * c_in]
+        feat = plane.reshape(n_images, H + 2, W + 2, c_in)[:, 1:-1, 1:-1].permute(0, 3, 1, 2)
+        sh = th.nn.functional.pixel_shuffle(feat.float(), r)  # (n, c_in/r^2, H*r, W*r)
+        o[:, pl * c_out_pad:pl * c_out_pad + sh.shape[1]] = sh.permute(0, 2, 3, 1).reshape(-1, sh.shape[1]).to(out.dtype)
     return out
 
 
@@ -113,32 +130,33 @@ class FakeLauncher:
         d = ref._obj
         self.calls.append("gd_conv_taps_bf16")
         inp, W, out = self._t(d.inp), self._t(d.W), self._t(d.out)
-        assert inp.shape[1] == d.c_in and W.shape == (d.c_out, d.n_taps * d.c_in) and d.out_ld == d.c_out
-        out2 = out.view(-1, d.c_out)
-        conv_taps_ref(inp, W, d.n_images, d.grid_h, d.grid_w, [d.tap_shift[i] for i in range(d.n_taps)], self._t(d.bias),
-                      self._t(d.scale), self._t(d.shift), d.relu, (d.y0, d.y1, d.x0, d.x1), d.stride, out2,
-                      (d.out_img_stride, d.out_y_stride, d.out_x_stride, d.out_offset))
+        assert inp.shape[1] == d.in_ld and W.shape == (d.c_out, d.n_taps * d.k_per_tap)
+        assert d.in_ld % 64 == 0 and d.k_per_tap % 64 == 0 and d.c_out % 64 == 0 and d.c_store % 32 == 0
+        out2 = out.view(-1, d.out_ld)
+        conv_taps_ref(inp, W, d.n_images, d.grid_h, d.grid_w, [d.tap_shift[i] for i in range(d.n_taps)], d.k_per_tap,
+                      self._t(d.bias), self._t(d.scale), self._t(d.shift), d.relu, (d.y0, d.y1, d.x0, d.x1), d.stride, out2,
+                      (d.out_img_stride, d.out_y_stride, d.out_x_stride, d.out_offset), d.c_store, d.split_out)
         return 0
 
-    def gd_speech_stem(self, mel, w, b, sc, sh, out, n, H, W, c_real, c_pad, stream):
+    def gd_speech_stem(self, mel, w, b, sc, sh, out, n, H, W, c_real, c_pad, split, stream):
         self.calls.append("gd_speech_stem")
-        stem_ref(self._t(mel)[:n], self._t(w), self._t(b), self._t(sc), self._t(sh), self._t(out), c_pad)
+        stem_ref(self._t(mel)[:n], self._t(w), self._t(b), self._t(sc), self._t(sh), self._t(out), c_pad, split)
         return 0
 
-    def gd_se_gate(self, y, n, gh, gw, c, c_real, c_hidden, w1, b1, w2, b2, gate, stream):
+    def gd_se_gate(self, y, n, gh, gw, c, split, c_real, c_hidden, w1, b1, w2, b2, gate, stream):
         self.calls.append("gd_se_gate")
         assert self._t(w1).shape == (c_hidden, c_real)
-        se_gate_ref(self._t(y), n, gh, gw, c_real, self._t(w1), self._t(b1), self._t(w2), self._t(b2), self._t(gate))
+        se_gate_ref(self._t(y), n, gh, gw, c, split, c_real, self._t(w1), self._t(b1), self._t(w2), self._t(b2), self._t(gate))
         return 0
 
-    def gd_se_residual_relu(self, y, res, gate, out, n, gh, gw, c, stream):
+    def gd_se_residual_relu(self, y, res, gate, out, n, gh, gw, c, split, stream):
         self.calls.append("gd_se_residual_relu")
-        se_residual_relu_ref(self._t(y), self._t(res), self._t(gate), self._t(out), n, gh, gw)
+        se_residual_relu_ref(self._t(y), self._t(res), self._t(gate), self._t(out), n, gh, gw, c, split)
         return 0
 
-    def gd_pixel_shuffle_rows(self, inp, out, n, H, W, c_in, r, c_out_pad, stream):
+    def gd_pixel_shuffle_rows(self, inp, out, n, H, W, c_in, r, c_out_pad, split, stream):
         self.calls.append("gd_pixel_shuffle_rows")
-        pixel_shuffle_ref(self._t(inp), self._t(out), n, H, W, r, c_out_pad)
+        pixel_shuffle_ref(self._t(inp), self._t(out), n, H, W, c_in, r, c_out_pad, split)
         return 0
 
     def gd_last_error(self):
