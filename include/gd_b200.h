@@ -274,12 +274,15 @@ int gd_speech_stem(const float* mel, const float* w, const float* bias, const fl
                    void* stream);
 
 /* SELayer gate (ResNetBlocks.py:81-96): gate[img, c] = sigmoid(W2 · relu(W1 · mean_pixels(y[img]) + b1) + b2).
- * y: bf16 pixel rows on a bordered grid (border = 0), `c` channels per row of which the first c_real are real;
+ * y: pixel rows on a bordered grid (border = 0), `c` stored channels of which the first c_real are real;
  * w1 fp32 [c_hidden, c_real], w2 fp32 [c_real, c_hidden]; gate fp32 [n_images, c] (padding channels get 0).
- * Fixed summation order per image: the gate of a clip does not depend on the batch it is in. */
+ * The pixel sum is taken in fixed slices that depend on the grid only: the gate of a clip does not depend on the batch
+ * it is in.  `scratch`: at least gd_se_gate_scratch_bytes() bytes, zeroed once by the caller (the kernel leaves its
+ * counters at zero), not shared with a concurrently running gd_se_gate. */
+int64_t gd_se_gate_scratch_bytes(int32_t n_images, int32_t grid_h, int32_t grid_w, int32_t c);
 int gd_se_gate(const void* y_bf16, int32_t n_images, int32_t grid_h, int32_t grid_w, int32_t c, int32_t split, int32_t c_real,
                int32_t c_hidden, const float* w1, const float* b1, const float* w2, const float* b2, float* gate,
-               void* stream);
+               void* scratch, int64_t scratch_bytes, void* stream);
 
 /* Block tail (ResNetBlocks.py:30-36): out = relu(gate[img, c] * y + residual) on the interior pixels of the grid. */
 int gd_se_residual_relu(const void* y_bf16, const void* residual_bf16, const float* gate, void* out_bf16,

@@ -29,15 +29,24 @@ def timed(fn, reps=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="beat-ours")
+    ap.add_argument("--encoder-only", type=int, default=0, help="N: run the speech encoder on N clips twice and exit (ncu target)")
     args = ap.parse_args()
     params, C, T, L, clips = bench.workload_preset(args.workload)
     th.manual_seed(0)
     model, diffusion, *_ = create_model(C, params)
     model.eval().to("cuda")
+    if args.encoder_only:
+        clips = args.encoder_only
     shape = (clips, C, T)
     chain = chain_for(model, diffusion, shape, "ddpm", "cuda", use_graph=False)
     x_T = th.randn(shape, device="cuda")
     wav = synthetic_wav(clips, L).cuda()
+    if args.encoder_only:
+        for _ in range(2):
+            chain._speech_features(wav)
+        th.cuda.synchronize()
+        print("ok")
+        return
     row = {"workload": args.workload, "clips": clips, "encoder_chunk": chain.encoder_chunk}
     row["begin_ms"] = timed(lambda: chain.begin(x_T, wav))
     row["begin_no_tape_ms"] = timed(lambda: chain.begin(x_T, wav, need_tape=False))

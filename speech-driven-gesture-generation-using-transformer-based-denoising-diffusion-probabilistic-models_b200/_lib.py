@@ -71,7 +71,9 @@ SYMBOLS = {
     "gd_step_add": (c_i32, [c_vp, c_i32, c_vp]),
     "gd_conv_taps_bf16": (c_i32, [C.POINTER(ConvDesc), c_vp]),
     "gd_speech_stem": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
-    "gd_se_gate": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gd_se_gate_scratch_bytes": (C.c_int64, [c_i32, c_i32, c_i32, c_i32]),
+    "gd_se_gate": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                           C.c_int64, c_vp]),
     "gd_se_residual_relu": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "gd_pixel_shuffle_rows": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
 }

@@ -91,26 +91,32 @@ __global__ void __launch_bounds__(256) speech_stem_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------ squeeze-excite gate
-// One CTA per image: channel sums over every pixel row of the grid (the border is zero) in a fixed order, then the two
-// tiny Linear layers.  c <= 256.
+// grid (slices, images): a CTA sums the channels of SE_SLICE pixel rows of one image (the border is zero) in a fixed
+// order and writes its partial; the last CTA of an image to finish adds the partials in slice order and applies the two
+// tiny Linear layers.  The slicing depends on the image size only, so a clip's gate does not depend on its batch.
+constexpr int SE_SLICE = 256;
+
 __global__ void __launch_bounds__(256) se_gate_kernel(const __nv_bfloat16* __restrict__ y, int grid_px, int interior_px, int c,
                                                       int split, int c_real, int c_hidden, const float* __restrict__ w1,
                                                       const float* __restrict__ b1, const float* __restrict__ w2,
-                                                      const float* __restrict__ b2, float* __restrict__ gate) {
+                                                      const float* __restrict__ b2, float* __restrict__ gate,
+                                                      float* __restrict__ partial, int* __restrict__ counters) {
     __shared__ float s_part[256 * 8];
     __shared__ float s_mean[256];
     __shared__ float s_hid[32];
+    __shared__ int s_last;
     pdl_launch_dependents();
     pdl_wait();
-    const int img = blockIdx.x;
+    const int img = blockIdx.y, slice = blockIdx.x, slices = gridDim.x;
     const int groups = c >> 3;            // 8-channel groups per pixel row
     const int lanes = 256 / groups;       // pixel rows read concurrently
     const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const int ld = split ? 2 * c : c;
     const __nv_bfloat16* base = y + (size_t)img * grid_px * ld;
+    const int p_end = min(grid_px, (slice + 1) * SE_SLICE);
     if (pl < lanes) {
-        for (int p = pl; p < grid_px; p += lanes) {
+        for (int p = slice * SE_SLICE + pl; p < p_end; p += lanes) {
             float f[8];
             load_ch8(base + (size_t)p * ld, c, g, split, f);
 #pragma unroll
@@ -120,11 +126,27 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const __nv_bfloat16* __res
 #pragma unroll
     for (int j = 0; j < 8; ++j) s_part[threadIdx.x * 8 + j] = acc[j];
     __syncthreads();
+    float* my_partials = partial + (size_t)img * slices * c;
     if (threadIdx.x < c) {
         const int ch = threadIdx.x, cg = ch >> 3, cj = ch & 7;
         float s = 0.f;
         for (int l = 0; l < lanes; ++l) s += s_part[(l * groups + cg) * 8 + cj];
-        s_mean[ch] = s / (float)interior_px;
+        my_partials[slice * c + ch] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int done = atomicAdd(&counters[img], 1);
+        s_last = (done == slices - 1);
+        if (s_last) counters[img] = 0;  // ready for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < c) {
+        float s = 0.f;
+        for (int sl = 0; sl < slices; ++sl) s += __ldcg(my_partials + sl * c + threadIdx.x);
+        s_mean[threadIdx.x] = s / (float)interior_px;
     }
     __syncthreads();
     if (threadIdx.x < c_hidden) {
@@ -229,16 +251,27 @@ extern "C" int gd_speech_stem(const float* mel, const float* w, const float* bia
     return GD_OK;
 }
 
+extern "C" int64_t gd_se_gate_scratch_bytes(int32_t n_images, int32_t grid_h, int32_t grid_w, int32_t c) {
+    const int64_t slices = ((int64_t)grid_h * grid_w + SE_SLICE - 1) / SE_SLICE;
+    return 4 * (((int64_t)n_images + 3) / 4 * 4 + (int64_t)n_images * slices * c);
+}
+
 extern "C" int gd_se_gate(const void* y_bf16, int32_t n_images, int32_t grid_h, int32_t grid_w, int32_t c, int32_t split,
                           int32_t c_real, int32_t c_hidden, const float* w1, const float* b1, const float* w2, const float* b2, float* gate,
-                          void* stream) {
-    if (!y_bf16 || !w1 || !b1 || !w2 || !b2 || !gate) return set_error(GD_ERR_INVALID, "gd_se_gate: null pointer");
+                          void* scratch, int64_t scratch_bytes, void* stream) {
+    if (!y_bf16 || !w1 || !b1 || !w2 || !b2 || !gate || !scratch) return set_error(GD_ERR_INVALID, "gd_se_gate: null pointer");
     if (n_images <= 0 || grid_h < 3 || grid_w < 3 || c < 32 || c > 256 || (c & (c - 1)) || c_real <= 0 || c_real > c ||
         c_hidden <= 0 || c_hidden > 32)
         return set_error(GD_ERR_INVALID, "gd_se_gate: bad shape (c in {32,64,128,256}, c_hidden <= 32)");
-    GD_CUDA_CHECK(launch_k(se_gate_kernel, n_images, 256, 0, reinterpret_cast<cudaStream_t>(stream), 1,
+    const int slices = (grid_h * grid_w + SE_SLICE - 1) / SE_SLICE;
+    if (scratch_bytes < gd_se_gate_scratch_bytes(n_images, grid_h, grid_w, c))
+        return set_error(GD_ERR_INVALID, "gd_se_gate: scratch too small (see gd_se_gate_scratch_bytes)");
+    if (n_images > 65535) return set_error(GD_ERR_INVALID, "gd_se_gate: at most 65535 images per launch");
+    int* counters = reinterpret_cast<int*>(scratch);
+    float* partial = reinterpret_cast<float*>(scratch) + ((n_images + 3) & ~3);
+    GD_CUDA_CHECK(launch_k(se_gate_kernel, dim3(slices, n_images), 256, 0, reinterpret_cast<cudaStream_t>(stream), 1,
                            reinterpret_cast<const __nv_bfloat16*>(y_bf16), grid_h * grid_w, (grid_h - 2) * (grid_w - 2), c,
-                           split, c_real, c_hidden, w1, b1, w2, b2, gate));
+                           split, c_real, c_hidden, w1, b1, w2, b2, gate, partial, counters));
     count_launch();
     GD_CUDA_CHECK(cudaGetLastError());
     return GD_OK;

@@ -487,8 +487,8 @@ class SamplingChain:
                 # same generator stream.  Loop position k uses index i = n-1-k.
                 if self.tape is None or self.tape.shape != tape_shape:
                     self.tape = th.empty(tape_shape, device=dev)
-                for k in range(self.n_steps):
-                    self.tape[self.n_steps - 1 - k] = th.randn_like(self.x)
+                for k in range(self.n_steps):  # in place: same generator stream as randn_like, no staging copy
+                    self.tape[self.n_steps - 1 - k].normal_()
             else:
                 assert tuple(noise_tape.shape) == tape_shape, f"noise_tape must be {tape_shape}"
                 tp = noise_tape.to(dev).float().flip(0).contiguous()  # loop order -> index order

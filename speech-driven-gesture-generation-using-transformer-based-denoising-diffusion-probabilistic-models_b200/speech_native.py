@@ -122,7 +122,7 @@ class _Head:
 class NativeSpeechEncoder:
     """`SpeechEncoder.forward` on libgd_b200.so.  `chunk` clips go through the trunk at a time (workspace ~8 MB per clip)."""
 
-    MEL_CHUNK = 16  # the mel front end runs in fixed micro-batches (library FFT / matmul pick algorithms per batch size)
+    MEL_CHUNK = 64  # the mel front end runs in fixed micro-batches (library FFT / matmul pick algorithms per batch size)
 
     def __init__(self, enc, launcher, device, chunk=64, precision="bf16x3"):
         if precision not in ("bf16x3", "bf16"):
@@ -165,7 +165,8 @@ class NativeSpeechEncoder:
             c, rows = blocks[0].c, n * (H + 2) * (W + 2)
             ld = planes * c
             stages.append({"H": H, "W": W, "c": c, "x": [z(rows, ld), z(rows, ld)], "y1": z(rows, ld), "y2": z(rows, ld),
-                           "r": z(rows, ld) if blocks[0].down is not None else None, "gate": z(n, c, th.float32)})
+                           "r": z(rows, ld) if blocks[0].down is not None else None, "gate": z(n, c, th.float32),
+                           "scratch": z(int(self.lib.gd_se_gate_scratch_bytes(n, H + 2, W + 2, c)) // 4, 1, th.float32)})
         heads = []
         for k, hd in enumerate(self.heads):
             st = stages[k + 1]
@@ -221,7 +222,8 @@ class NativeSpeechEncoder:
                     self._same_conv(blk.down, x, n, in_hw, g["r"], hw)
                     res = g["r"]
                 gd.check(lib.gd_se_gate(_p(g["y2"]), n, hw[0] + 2, hw[1] + 2, c, sp, blk.c_real, blk.c_hidden,
-                                        *[_p(t) for t in blk.se], _p(g["gate"]), s), "gd_se_gate")
+                                        *[_p(t) for t in blk.se], _p(g["gate"]), _p(g["scratch"]), g["scratch"].numel() * 4, s),
+                         "gd_se_gate")
                 out = g["x"][1] if x is g["x"][0] else g["x"][0]
                 gd.check(lib.gd_se_residual_relu(_p(g["y2"]), _p(res), _p(g["gate"]), _p(out), n, hw[0] + 2, hw[1] + 2, c, sp, s),
                          "gd_se_residual_relu")

@@ -143,8 +143,13 @@ class FakeLauncher:
         stem_ref(self._t(mel)[:n], self._t(w), self._t(b), self._t(sc), self._t(sh), self._t(out), c_pad, split)
         return 0
 
-    def gd_se_gate(self, y, n, gh, gw, c, split, c_real, c_hidden, w1, b1, w2, b2, gate, stream):
+    @staticmethod
+    def gd_se_gate_scratch_bytes(n, gh, gw, c):
+        return 4 * ((n + 3) // 4 * 4 + n * ((gh * gw + 255) // 256) * c)
+
+    def gd_se_gate(self, y, n, gh, gw, c, split, c_real, c_hidden, w1, b1, w2, b2, gate, scratch, scratch_bytes, stream):
         self.calls.append("gd_se_gate")
+        assert scratch_bytes >= self.gd_se_gate_scratch_bytes(n, gh, gw, c)
         assert self._t(w1).shape == (c_hidden, c_real)
         se_gate_ref(self._t(y), n, gh, gw, c, split, c_real, self._t(w1), self._t(b1), self._t(w2), self._t(b2), self._t(gate))
         return 0

@@ -19,7 +19,7 @@ from gesture_b200.presets import BEAT_OURS, TEDEXP_OURS, preset
 
 def test_cabi_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "gd_b200.h")).read()
-    declared = set(re.findall(r"^\s*(?:int|const char\*|uint64_t)\s+(gd_\w+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^\s*(?:int|const char\*|uint64_t|int64_t)\s+(gd_\w+)\s*\(", header, flags=re.M))
     assert {"gd_linear_bf16", "gd_linear_ddpm", "gd_ddpm_update", "gd_layernorm", "gd_dconv_attention"} <= declared
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     lib = ctypes.CDLL(_lib.LIB_PATH)

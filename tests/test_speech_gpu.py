@@ -166,8 +166,14 @@ def test_stem_gate_tail_shuffle(gd, split):
         w1, b1 = th.randn(ch, cr, device="cuda", generator=g) / math.sqrt(cr), th.randn(ch, device="cuda", generator=g)
         w2, b2 = th.randn(cr, ch, device="cuda", generator=g) / math.sqrt(ch), th.randn(cr, device="cuda", generator=g)
         gate = th.full((ni, cc), -1.0, device="cuda")
-        gd.check(lib.gd_se_gate(y.data_ptr(), ni, gh, gw, cc, split, cr, ch, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
-                                b2.data_ptr(), gate.data_ptr(), _stream()), "gd_se_gate")
+        scratch = th.zeros(lib.gd_se_gate_scratch_bytes(ni, gh, gw, cc) // 4, device="cuda")
+        for _ in range(2):  # twice: the kernel must leave its counters ready for the next launch
+            gd.check(lib.gd_se_gate(y.data_ptr(), ni, gh, gw, cc, split, cr, ch, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                                    b2.data_ptr(), gate.data_ptr(), scratch.data_ptr(), scratch.numel() * 4, _stream()), "gd_se_gate")
+        with pytest.raises(gd.GdError):
+            lib_rc = lib.gd_se_gate(y.data_ptr(), ni, gh, gw, cc, split, cr, ch, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                                    b2.data_ptr(), gate.data_ptr(), scratch.data_ptr(), 16, _stream())
+            gd.check(lib_rc, "gd_se_gate")
         want_gate = ref.se_gate_ref(y, ni, gh, gw, cc, split, cr, w1, b1, w2, b2, th.zeros_like(gate))
         assert (gate - want_gate).abs().max().item() < 1e-4
         # block tail
