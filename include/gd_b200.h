@@ -219,7 +219,7 @@ int gd_cast_rows_bf16(const float* src, int32_t lds, void* dst, int32_t ldd, int
 
 /* ------------------------------------------------------------------------------------------
  * Speech encoder (once per clip): HA2GSpeechEncoder `models/modules/ha2g/speech_encoder.py:37-61` over the ResNetSE-34
- * trunk `models/modules/ha2g/model/ResNetSE34V2.py:118-186` with SEBasicBlock / SELayer `.../ResNetBlocks.py:7-37,81-96`.
+ * trunk `models/modules/ha2g/model/ResNetSE34V2.py:118-189` with SEBasicBlock / SELayer `.../ResNetBlocks.py:7-37,81-96`.
  *
  * Feature maps are channel-last bf16 "pixel rows" over a zero-bordered grid: row = image*(grid_h*grid_w) + y*grid_w + x,
  * c channels contiguous - one bf16 plane [c] (`split` = 0) or two planes [hi(c) | lo(c)] with value = hi + lo
@@ -288,7 +288,7 @@ int gd_se_gate(const void* y_bf16, int32_t n_images, int32_t grid_h, int32_t gri
 int gd_se_residual_relu(const void* y_bf16, const void* residual_bf16, const float* gate, void* out_bf16,
                         int32_t n_images, int32_t grid_h, int32_t grid_w, int32_t c, int32_t split, void* stream);
 
-/* nn.PixelShuffle(r) (ResNetSE34V2.py:169-170,181-182) from a bordered grid (H+2) x (W+2) with c_in channels to an
+/* nn.PixelShuffle(r) (ResNetSE34V2.py:167-168,179-180) from a bordered grid (H+2) x (W+2) with c_in channels to an
  * unbordered (H*r) x (W*r) grid with c_in/r^2 real channels zero-padded to c_out_pad. */
 int gd_pixel_shuffle_rows(const void* in_bf16, void* out_bf16, int32_t n_images, int32_t H, int32_t W, int32_t c_in,
                           int32_t r, int32_t c_out_pad, int32_t split, void* stream);

@@ -1,5 +1,5 @@
 """Once-per-clip speech encoder on our kernels: the ResNetSE-34 trunk and the three pyramid heads of
-`HA2GSpeechEncoder` (reference `models/modules/ha2g/speech_encoder.py:37-61`, `.../model/ResNetSE34V2.py:118-186`,
+`HA2GSpeechEncoder` (reference `models/modules/ha2g/speech_encoder.py:37-61`, `.../model/ResNetSE34V2.py:118-189`,
 `.../model/ResNetBlocks.py:7-37,81-96`) as tensor-core implicit-GEMM convolutions (`gd_conv_taps_bf16`) plus the row
 kernels of csrc/speech_kernels.cu.  The module packs the weights of a `modules.SpeechEncoder` (the state_dict-compatible
 parameter holder) once, owns the feature-map workspace and turns wav (N, T_wav) into the three (N, T_k, d_model)
