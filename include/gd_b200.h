@@ -266,6 +266,19 @@ typedef struct gd_conv_desc {
 
 int gd_conv_taps_bf16(const gd_conv_desc* d, void* stream);
 
+/* Mel front end of HA2GSpeechEncoder (speech_encoder.py:18-27,50; PreEmphasis ha2g/model/utils.py:22-37;
+ * torchaudio MelSpectrogram(16 kHz, n_fft 1024, hop 512, 128 HTK mel bins, power 2, centre reflect padding)):
+ *   y[t] = wav[t] - preemph * wav[t-1] (reflect pad 1);  S = |STFT(y, periodic Hann `window`[1024])|^2;
+ *   mel[clip, m, frame] = sum_k S[k, frame] * fb[k, m] + add_eps          frames = wav_len/512 + 1
+ * twiddle: fp32 [512][2] = (cos, -sin)(2*pi*k/1024); fb: fp32 [513, 128] (`mel_scale.fb`); fb_range: int32 [128][2] =
+ * first / last frequency bin with a non-zero weight per mel bin.  Fixed n_fft / hop / bins as in the reference. */
+int gd_mel_power(const float* wav, int32_t n_clips, int32_t wav_len, const float* window, const float* twiddle,
+                 const float* fb, const int32_t* fb_range, float preemph, float add_eps, float* mel, void* stream);
+
+/* nn.InstanceNorm1d(128) (speech_encoder.py:28,51): every row of `len` values (one mel bin of one clip over time) is
+ * normalised in place with its own mean and biased variance. */
+int gd_instance_norm_rows(float* x, int32_t rows, int32_t len, float eps, void* stream);
+
 /* Stem: conv1 (1 -> c_real channels, 3x3, bias) + ReLU + BatchNorm (ResNetSE34V2.py:127-129) on the normalised mel image
  * mel fp32 (n_images, H, W) -> bf16 pixel rows on the (H+2) x (W+2) bordered grid, channels [c_real, c_pad) written as 0.
  *   w fp32 [c_real, 9], bias / scale / shift fp32 [c_real]. */

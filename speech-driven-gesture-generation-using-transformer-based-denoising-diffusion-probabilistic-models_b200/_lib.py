@@ -70,6 +70,8 @@ SYMBOLS = {
     "gd_cast_rows_bf16": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "gd_step_add": (c_i32, [c_vp, c_i32, c_vp]),
     "gd_conv_taps_bf16": (c_i32, [C.POINTER(ConvDesc), c_vp]),
+    "gd_mel_power": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_f32, c_f32, c_vp, c_vp]),
+    "gd_instance_norm_rows": (c_i32, [c_vp, c_i32, c_i32, c_f32, c_vp]),
     "gd_speech_stem": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "gd_se_gate_scratch_bytes": (C.c_int64, [c_i32, c_i32, c_i32, c_i32]),
     "gd_se_gate": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,

@@ -303,3 +303,104 @@ extern "C" int gd_pixel_shuffle_rows(const void* in_bf16, void* out_bf16, int32_
     GD_CUDA_CHECK(cudaGetLastError());
     return GD_OK;
 }
+
+// ------------------------------------------------------------------------------------------ mel front end
+// HA2GSpeechEncoder's wav2spec (speech_encoder.py:18-27,50): pre-emphasis (reflect pad 1), STFT n_fft 1024 / hop 512 /
+// periodic Hann / centre reflect padding, power spectrum, 128-bin HTK mel filterbank, + eps.  One CTA per (clip, frame):
+// the 1024 windowed samples go through an in-place radix-2 FFT in shared memory (fp32, host-computed float64 twiddles),
+// then every mel bin sums its own (contiguous) band of the power spectrum.
+namespace gd {
+
+constexpr int MEL_NFFT = 1024, MEL_HOP = 512, MEL_BINS = 128, MEL_FREQS = MEL_NFFT / 2 + 1;
+
+__global__ void __launch_bounds__(256) mel_power_kernel(const float* __restrict__ wav, int wav_len, int frames,
+                                                        const float* __restrict__ window, const float2* __restrict__ twiddle,
+                                                        const float* __restrict__ fb, const int2* __restrict__ fb_range,
+                                                        float preemph, float add_eps, float* __restrict__ mel) {
+    __shared__ float2 s[MEL_NFFT];
+    __shared__ float2 s_tw[MEL_NFFT / 2];
+    __shared__ float s_pow[MEL_FREQS];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int clip = blockIdx.x / frames, frame = blockIdx.x - clip * frames;
+    const float* x = wav + (size_t)clip * wav_len;
+    for (int i = threadIdx.x; i < MEL_NFFT / 2; i += 256) s_tw[i] = __ldg(twiddle + i);
+    for (int i = threadIdx.x; i < MEL_NFFT; i += 256) {
+        int j = frame * MEL_HOP + i - MEL_NFFT / 2;      // sample index of the pre-emphasised signal, reflect-padded
+        if (j < 0) j = -j;
+        if (j >= wav_len) j = 2 * (wav_len - 1) - j;
+        const float cur = __ldg(x + j), prev = __ldg(x + (j > 0 ? j - 1 : 1));
+        const float y = cur - preemph * prev;
+        s[__brev((unsigned)i) >> 22] = make_float2(y * __ldg(window + i), 0.f);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int half = 1; half < MEL_NFFT; half <<= 1) {
+        const int tw_step = (MEL_NFFT / 2) / half;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int b = threadIdx.x + r * 256;
+            const int j = b & (half - 1);
+            const int i0 = ((b - j) << 1) + j, i1 = i0 + half;
+            const float2 w = s_tw[j * tw_step], a = s[i0], c = s[i1];
+            const float tr = w.x * c.x - w.y * c.y, ti = w.x * c.y + w.y * c.x;
+            s[i0] = make_float2(a.x + tr, a.y + ti);
+            s[i1] = make_float2(a.x - tr, a.y - ti);
+        }
+        __syncthreads();
+    }
+    for (int k = threadIdx.x; k < MEL_FREQS; k += 256) s_pow[k] = s[k].x * s[k].x + s[k].y * s[k].y;
+    __syncthreads();
+    if (threadIdx.x < MEL_BINS) {
+        const int m = threadIdx.x;
+        const int2 rg = __ldg(fb_range + m);  // [first, last] frequency bin with a non-zero weight
+        float acc = 0.f;
+        for (int k = rg.x; k <= rg.y; ++k) acc = fmaf(s_pow[k], __ldg(fb + k * MEL_BINS + m), acc);
+        mel[((size_t)clip * MEL_BINS + m) * frames + frame] = acc + add_eps;
+    }
+}
+
+// nn.InstanceNorm1d (no affine, biased variance): one warp per row, two passes over the row (L1-resident).
+__global__ void __launch_bounds__(256) instance_norm_rows_kernel(float* __restrict__ x, int rows, int len, float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float* p = x + (size_t)row * len;
+    float s = 0.f;
+    for (int i = lane; i < len; i += 32) s += p[i];
+    const float mean = warp_sum(s) / (float)len;
+    float q = 0.f;
+    for (int i = lane; i < len; i += 32) {
+        const float d = p[i] - mean;
+        q += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)len + eps);
+    for (int i = lane; i < len; i += 32) p[i] = (p[i] - mean) * rstd;
+}
+
+}  // namespace gd
+
+extern "C" int gd_mel_power(const float* wav, int32_t n_clips, int32_t wav_len, const float* window, const float* twiddle,
+                            const float* fb, const int32_t* fb_range, float preemph, float add_eps, float* mel,
+                            void* stream) {
+    if (!wav || !window || !twiddle || !fb || !fb_range || !mel) return set_error(GD_ERR_INVALID, "gd_mel_power: null pointer");
+    if (n_clips <= 0 || wav_len <= MEL_NFFT / 2) return set_error(GD_ERR_INVALID, "gd_mel_power: wav_len must exceed 512 samples");
+    const int frames = wav_len / MEL_HOP + 1;
+    if ((int64_t)n_clips * frames >= ((int64_t)1 << 31)) return set_error(GD_ERR_INVALID, "gd_mel_power: too many frames");
+    GD_CUDA_CHECK(launch_k(mel_power_kernel, n_clips * frames, 256, 0, reinterpret_cast<cudaStream_t>(stream), 1, wav, wav_len,
+                           frames, window, reinterpret_cast<const float2*>(twiddle), fb, reinterpret_cast<const int2*>(fb_range),
+                           preemph, add_eps, mel));
+    count_launch();
+    GD_CUDA_CHECK(cudaGetLastError());
+    return GD_OK;
+}
+
+extern "C" int gd_instance_norm_rows(float* x, int32_t rows, int32_t len, float eps, void* stream) {
+    if (!x || rows <= 0 || len <= 0) return set_error(GD_ERR_INVALID, "gd_instance_norm_rows: bad argument");
+    GD_CUDA_CHECK(launch_k(instance_norm_rows_kernel, (rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream), 1, x, rows,
+                           len, eps));
+    count_launch();
+    GD_CUDA_CHECK(cudaGetLastError());
+    return GD_OK;
+}

@@ -15,6 +15,7 @@ positive `graph_steps` captures that many consecutive steps per graph instead.
 """
 import ctypes as C
 import math
+import os
 
 import torch as th
 
@@ -208,7 +209,6 @@ class SamplingChain:
         self.xa_add = None  # Inpaint model: (N,C,T) offset added when the bf16 emb_x operand is built
         self.plan = None
         self.side = th.cuda.Stream(device=device)
-        import os
         env = os.environ.get  # GD_CONCURRENT / GD_FUSE_LN = 0|1 override the model attributes (A/B measurements)
         self.concurrent = bool(int(env("GD_CONCURRENT", int(getattr(model, "concurrent_streams", True)))))
         # Residual GEMM + following LayerNorm in one kernel (gd_linear_resid_ln).  Off by default: measured on B200 inside
@@ -244,12 +244,13 @@ class SamplingChain:
         try:
             if self.speech_impl != "torch":  # ResNetSE-34 trunk + heads on our kernels (speech_native.py)
                 precision = "bf16" if self.speech_impl == "native-bf16" else "bf16x3"
-                key = (self.model.weights_version, str(self.device), self.native_encoder_chunk, precision)
+                mel_impl = os.environ.get("GD_MEL", getattr(self.model, "mel_impl", "native"))
+                key = (self.model.weights_version, str(self.device), self.native_encoder_chunk, precision, mel_impl)
                 cached = getattr(self.model, "_native_speech", None)  # packed once per (weights, device), shared by chains
                 if cached is None or cached[0] != key:
                     from .speech_native import NativeSpeechEncoder
                     cached = (key, NativeSpeechEncoder(enc, self.L, self.device, chunk=self.native_encoder_chunk,
-                                                       precision=precision))
+                                                       precision=precision, mel_impl=mel_impl))
                     self.model._native_speech = cached
                 return cached[1](wav)
             # fixed-size micro-batches (last one zero-padded): cuDNN then runs the same algorithm whatever the batch

@@ -16,10 +16,12 @@ precision is therefore "bf16x3": feature maps are stored as two bf16 planes [hi 
 the same way on the host, and each convolution accumulates hi*Whi + lo*Whi + hi*Wlo in fp32 on the tensor cores -
 fp32-class products at a third of the bf16 rate.  "bf16" (one plane, narrow layers zero-padded to 64 channels) is kept
 as the fast option.  Every kernel treats pixel rows independently and reduces in a fixed order, so a clip's features do
-not depend on its batch.  The mel front end (pre-emphasis, STFT, mel filterbank, InstanceNorm1d) is evaluated by
-`SpeechEncoder.wav2spec` in fixed micro-batches.
+not depend on its batch.  The mel front end (pre-emphasis, STFT, mel filterbank, InstanceNorm1d) runs on two kernels of
+its own (`gd_mel_power`: one shared-memory fp32 FFT per frame; `gd_instance_norm_rows`); `mel_impl="torch"` evaluates
+`SpeechEncoder.wav2spec` (torch.stft) in fixed micro-batches instead.
 """
 import ctypes as C
+import math
 
 import torch as th
 
@@ -124,10 +126,14 @@ class NativeSpeechEncoder:
 
     MEL_CHUNK = 64  # the mel front end runs in fixed micro-batches (library FFT / matmul pick algorithms per batch size)
 
-    def __init__(self, enc, launcher, device, chunk=64, precision="bf16x3"):
+    def __init__(self, enc, launcher, device, chunk=64, precision="bf16x3", mel_impl="native"):
         if precision not in ("bf16x3", "bf16"):
             raise ValueError(f"speech precision must be 'bf16x3' or 'bf16', got {precision!r}")
+        if mel_impl not in ("native", "torch"):
+            raise ValueError(f"mel_impl must be 'native' or 'torch', got {mel_impl!r}")
         self.enc, self.L, self.lib, self.dev, self.chunk = enc, launcher, launcher.lib, device, chunk
+        self.mel_impl = mel_impl
+        self._pack_front_end()
         self.split = split = int(precision == "bf16x3")
         r = enc.wav_encoder.feat_extractor
         self.d = enc.wav_proj_layer.out_features
@@ -148,6 +154,24 @@ class NativeSpeechEncoder:
                       _Head(r.conv_mid, r.bn_mid, r.fc_mid, proj, 2, self.shuffle_c, 62, split),
                       _Head(r.conv_high, r.bn_high, r.fc_high, proj, 4, self.shuffle_c, 62, split)]
         self._ws = {}
+
+    def _pack_front_end(self):
+        """Buffers of the mel kernel: the module's own Hann window and filterbank (state_dict buffers), float64 twiddles,
+        and the non-zero band of every mel filter."""
+        pre, ms = self.enc.wav2spec[0], self.enc.wav2spec[1]
+        assert ms.spectrogram.n_fft == 1024 and ms.spectrogram.hop == 512, "the mel kernel is built for n_fft 1024 / hop 512"
+        self.window = ms.spectrogram.window.detach().float().contiguous()
+        self.fb = ms.mel_scale.fb.detach().float().contiguous()
+        assert tuple(self.fb.shape) == (513, 128)
+        k = th.arange(512, dtype=th.float64) * (2.0 * math.pi / 1024.0)
+        self.twiddle = th.stack([th.cos(k), -th.sin(k)], dim=1).float().to(self.fb.device).contiguous()
+        nz = self.fb != 0
+        idx = th.arange(513, device=self.fb.device)[:, None].expand(513, 128)
+        first = th.where(nz, idx, th.full_like(idx, 513)).min(dim=0).values
+        last = th.where(nz, idx, th.full_like(idx, -1)).max(dim=0).values
+        first = th.where(last < 0, th.zeros_like(first), first)  # an all-zero filter sums nothing: [0, -1]
+        self.fb_range = th.stack([first, last], dim=1).to(th.int32).contiguous()
+        self.preemph = -float(pre.flipped_filter.detach().reshape(-1)[0])
 
     # ------------------------------------------------------------------ workspace
     def _workspace(self, n, F):
@@ -249,6 +273,17 @@ class NativeSpeechEncoder:
         return outs
 
     def _mel(self, wav):
+        if self.mel_impl == "native":  # speech_kernels.cu: per-frame FFT + mel bands, then InstanceNorm1d rows, in place
+            w = wav.float().contiguous()
+            n, length = w.shape
+            frames = length // 512 + 1
+            mel = th.empty(n, 128, frames, device=self.dev, dtype=th.float32)
+            s = self.L.stream()
+            gd.check(self.lib.gd_mel_power(_p(w), n, length, _p(self.window), _p(self.twiddle), _p(self.fb), _p(self.fb_range),
+                                           self.preemph, 1e-6, _p(mel), s), "gd_mel_power")
+            gd.check(self.lib.gd_instance_norm_rows(_p(mel), n * 128, frames, self.enc.mel_spec_norm.eps, s),
+                     "gd_instance_norm_rows")
+            return mel
         enc, chunk, outs = self.enc, self.MEL_CHUNK, []
         for lo in range(0, wav.shape[0], chunk):
             w = wav[lo:lo + chunk].float()

@@ -97,6 +97,21 @@ def pixel_shuffle_ref(inp, out, n_images, H, W, c_in, r, c_out_pad, split=0):
     return out
 
 
+def mel_power_ref(wav, window, fb, preemph, add_eps):
+    """gd_mel_power: pre-emphasis (reflect pad 1) -> |STFT|^2 (n_fft 1024, hop 512, centre reflect) -> mel filterbank + eps."""
+    x = th.nn.functional.pad(wav[:, None], (1, 0), "reflect")[:, 0]
+    y = x[:, 1:] - preemph * x[:, :-1]
+    spec = th.stft(y, 1024, hop_length=512, win_length=1024, window=window, center=True, pad_mode="reflect",
+                   normalized=False, onesided=True, return_complex=True).abs().pow(2.0)
+    return th.matmul(spec.transpose(-1, -2), fb).transpose(-1, -2) + add_eps
+
+
+def instance_norm_ref(x, eps):
+    mean = x.mean(dim=-1, keepdim=True)
+    var = x.var(dim=-1, unbiased=False, keepdim=True)
+    return (x - mean) / th.sqrt(var + eps)
+
+
 class FakeLauncher:
     """Stands in for engine._Launcher + libgd_b200.so on CPU: every 'kernel' is the torch statement above.  Tensors are
     found through the pointers the host code puts into the descriptors (registered by `track`)."""
@@ -162,6 +177,24 @@ class FakeLauncher:
     def gd_pixel_shuffle_rows(self, inp, out, n, H, W, c_in, r, c_out_pad, split, stream):
         self.calls.append("gd_pixel_shuffle_rows")
         pixel_shuffle_ref(self._t(inp), self._t(out), n, H, W, c_in, r, c_out_pad, split)
+        return 0
+
+    def gd_mel_power(self, wav, n, length, window, twiddle, fb, fb_range, preemph, add_eps, mel, stream):
+        self.calls.append("gd_mel_power")
+        fbt, rg = self._t(fb), self._t(fb_range)
+        for m in range(128):  # the band table must cover every non-zero weight
+            lo, hi = int(rg[m, 0]), int(rg[m, 1])
+            assert fbt[:lo, m].abs().sum() == 0 and fbt[hi + 1:, m].abs().sum() == 0
+        tw = self._t(twiddle).double()
+        k = th.arange(512, dtype=th.float64) * (2 * th.pi / 1024)
+        assert (tw[:, 0] - th.cos(k)).abs().max() < 1e-7 and (tw[:, 1] + th.sin(k)).abs().max() < 1e-7
+        self._t(mel).copy_(mel_power_ref(self._t(wav)[:n, :length], self._t(window), fbt, preemph, add_eps))
+        return 0
+
+    def gd_instance_norm_rows(self, x, rows, length, eps, stream):
+        self.calls.append("gd_instance_norm_rows")
+        t = self._t(x)
+        t.copy_(instance_norm_ref(t.reshape(rows, length), eps).reshape(t.shape))
         return 0
 
     def gd_last_error(self):

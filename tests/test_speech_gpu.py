@@ -226,3 +226,36 @@ def test_native_encoder_matches_fp32_module(gd, d_model, n, wav_len, chunk, prec
         rel = ((a - b).norm() / a.norm()).item()
         assert rel < ENC_TOL[precision], (precision, rel)
         assert th.equal(b[n - 1:], c)
+
+
+@pytest.mark.parametrize("n,wav_len", [(3, 32000), (2, 36266), (1, 5000), (2, 128000)])
+def test_mel_front_end(gd, n, wav_len):
+    """gd_mel_power + gd_instance_norm_rows vs torch.stft / matmul / InstanceNorm1d, on noise and on a signal whose high
+    bands are 80 dB below the low ones (the per-bin normalisation amplifies errors in weak bands)."""
+    from gesture_b200.engine import _Launcher
+    from gesture_b200.modules import SpeechEncoder
+    from gesture_b200.speech_native import NativeSpeechEncoder
+    th.manual_seed(0)
+    enc = SpeechEncoder(256).eval().cuda()
+    native = NativeSpeechEncoder(enc, _Launcher(), th.device("cuda", 0))
+    g = th.Generator(device="cuda").manual_seed(n + wav_len)
+    noise = th.randn(n, wav_len, device="cuda", generator=g)
+    t = th.arange(wav_len, device="cuda") / 16000.0
+    voiced = sum(10.0 ** (-k / 2.0) * th.sin(2 * math.pi * 110.0 * (k + 1) * t * (1 + 0.01 * k)) for k in range(9))
+    voiced = voiced[None] * (1 + 0.5 * th.sin(2 * math.pi * 3.0 * t))[None] + 1e-4 * noise
+    for wav in (noise, voiced.expand(n, -1).contiguous()):
+        prev = th.backends.cuda.matmul.allow_tf32
+        th.backends.cuda.matmul.allow_tf32 = False
+        try:
+            with th.no_grad():
+                raw = enc.wav2spec(wav) + 1e-6
+                want = enc.mel_spec_norm(raw)
+        finally:
+            th.backends.cuda.matmul.allow_tf32 = prev
+        got = native._mel(wav)
+        assert got.shape == want.shape == (n, 128, wav_len // 512 + 1)
+        assert ((got - want).norm() / want.norm()).item() < 1e-4
+        assert (got - want).abs().max().item() < 5e-3   # unit-variance rows
+        # the un-normalised mel powers, checked through the reference statement used on CPU
+        raw2 = ref.mel_power_ref(wav, native.window, native.fb, native.preemph, 1e-6)
+        assert ((raw2 - raw).norm() / raw.norm()).item() < 1e-5

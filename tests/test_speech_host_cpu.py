@@ -48,6 +48,7 @@ def test_native_plan_matches_module_on_cpu(monkeypatch, n, frames, chunk, precis
         rel = ((a - b).norm() / a.norm()).item()
         assert rel < TOL[precision], (precision, rel)
     # 16 blocks x (2 convs + gate + tail) + 3 down-sample convs + 3 head convs + 2 shuffles + stem + 3 merged Linear layers
+    assert fake.calls.count("gd_mel_power") == 1 and fake.calls.count("gd_instance_norm_rows") == 1
     per_chunk = {"gd_conv_taps_bf16": 38, "gd_se_gate": 16, "gd_se_residual_relu": 16, "gd_pixel_shuffle_rows": 2,
                  "gd_speech_stem": 1, "gd_linear_bf16": 3}
     chunks = (n + chunk - 1) // chunk
