@@ -241,6 +241,12 @@ int gd_cast_rows_bf16(const float* src, int32_t lds, void* dst, int32_t ldd, int
  * sequence is hi, lo, hi; the host packs W per tap as [Whi | Whi | Wlo] and the GEMM accumulates
  * hi*Whi + lo*Whi + hi*Wlo in fp32 - the bf16x3 product, whose dropped term lo*Wlo is ~2^-18 relative.  With split_out
  * the epilogue stores channels [0, c_store) as [hi(c_store) | lo(c_store)].  Plain bf16: in_ld = k_per_tap = c_in.
+ * `walk` selects how the K dimension of a tap is laid out (same arithmetic, fewer operand loads):
+ *   0  generic: k-th element of a tap reads input column k mod in_ld (W as described above);
+ *   1  rows [hi(32) | lo(32)] (in_ld 64, k_per_tap 128): W per tap = [Whi|Whi | Wlo|0]; the input tile is loaded once and
+ *      multiplied by both 64-wide W blocks;
+ *   2  rows [hi(c) | lo(c)], c % 64 == 0 (k_per_tap = in_ld = 2c): W per tap and 64-channel block = [Whi(64) | Wlo(64)]; the hi
+ *      and lo tiles of the block are loaded once and the three products hi*Whi, lo*Whi, hi*Wlo are formed from them.
  * ------------------------------------------------------------------------------------------ */
 #define GD_CONV_MAX_TAPS 9
 typedef struct gd_conv_desc {
@@ -262,6 +268,7 @@ typedef struct gd_conv_desc {
     int32_t out_img_stride, out_y_stride, out_x_stride, out_offset;
     int32_t c_store;     /* output channels stored (multiple of 32, <= c_out)                   */
     int32_t split_out;   /* 0: [c_store] bf16;  1: [hi(c_store) | lo(c_store)]                  */
+    int32_t walk;        /* K layout of a tap: 0 generic wrap, 1 / 2 split rows with operand reuse */
 } gd_conv_desc;
 
 int gd_conv_taps_bf16(const gd_conv_desc* d, void* stream);

@@ -46,7 +46,7 @@ class ConvDesc(C.Structure):
                 ("bias", c_vp), ("scale", c_vp), ("shift", c_vp), ("relu", c_i32), ("y0", c_i32), ("y1", c_i32),
                 ("x0", c_i32), ("x1", c_i32), ("stride", c_i32), ("out", c_vp), ("out_ld", c_i32),
                 ("out_img_stride", c_i32), ("out_y_stride", c_i32), ("out_x_stride", c_i32), ("out_offset", c_i32),
-                ("c_store", c_i32), ("split_out", c_i32)]
+                ("c_store", c_i32), ("split_out", c_i32), ("walk", c_i32)]
 
 
 ACT_NONE, ACT_RELU2, ACT_SILU = 0, 1, 2

@@ -31,6 +31,10 @@ constexpr int MODE_DDPM = 1;      // final projection + DDPM update
 constexpr int MODE_TMA_BF16 = 2;  // bf16 output through TMA stores
 constexpr int MODE_TMA_F32 = 3;   // fp32 output through TMA stores, or TMA reduce-add when accumulating in place
 constexpr int MODE_CONV = 4;      // implicit-GEMM convolution over pixel rows (gd_conv_taps_bf16): shifted A tiles per tap
+// Split-precision convolutions with operand reuse: a pipeline stage holds the tiles of one (tap, 64-channel block) and the
+// MMA issuer forms all three bf16x3 products from them, so no tile is loaded twice (-1/3 shared-memory fill):
+constexpr int MODE_CONV_S1 = 5;   // rows [hi(32) | lo(32)]: 1 A tile, B tiles [Whi|Whi] and [Wlo|0]      -> A*B0 + A*B1
+constexpr int MODE_CONV_S2 = 6;   // rows [hi(c) | lo(c)], c % 64 == 0: A tiles hi, lo; B tiles Whi, Wlo  -> hi*Whi + lo*Whi + hi*Wlo
 
 struct GemmParams {
     int M, N, K;
@@ -58,11 +62,11 @@ struct GemmParams {
     int out_img_stride, out_y_stride, out_x_stride, out_offset;  // output row of a kept pixel
 };
 
-template <int BN, int CL>
+template <int BN, int CL, int NA = 1, int NB = 1>
 struct GemmCfg {
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
     static constexpr int B_BYTES = (BN / CL) * BLOCK_K * 2;  // a CTA of a pair stores half of the W tile
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGE_BYTES = NA * A_BYTES + NB * B_BYTES;  // NA / NB tiles per stage (MODE_CONV_S*: operand reuse)
     // per epilogue warp one 32-row x 32-column fp32 staging tile.  A deeper ring and a shared-memory copy of the bias were
     // measured and changed nothing (the epilogue is not waiting on them) while costing a pipeline stage, so: 4 KB / warp.
     static constexpr int STAGING_PER_WARP = 4096;
@@ -265,12 +269,14 @@ template <int BN, int MODE, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
-    using Cfg = GemmCfg<BN, CL>;
+    constexpr bool IS_CONV = MODE >= MODE_CONV;
+    constexpr int NA = (MODE == MODE_CONV_S2) ? 2 : 1, NB = (MODE >= MODE_CONV_S1) ? 2 : 1;
+    using Cfg = GemmCfg<BN, CL, NA, NB>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+    uint8_t* smem_b = smem + STAGES * NA * Cfg::A_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);  // 256 B reserved
     uint64_t* full_bar = bars;                    // [STAGES]  TMA -> MMA
     uint64_t* empty_bar = bars + STAGES;          // [STAGES]  MMA -> TMA
@@ -286,7 +292,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int m_groups = ((p.M + BLOCK_M - 1) / BLOCK_M + CL - 1) / CL;  // groups of CL consecutive m-tiles
     const int n_tiles = p.N / BN;
     const int num_tiles = m_groups * n_tiles;  // work items per cluster-wide scheduler
-    const int k_blocks = p.K / BLOCK_K;
+    const int k_blocks = p.K / (BLOCK_K * NB);  // pipeline stages per tile (a MODE_CONV_S* stage covers NB k-blocks of W)
     // work item `tile` -> this CTA's output tile; an m-tile past the end (odd tile count) is all out-of-bounds:
     // TMA zero-fills its loads and clips its stores, so the CTA just keeps the cluster protocol going
 #define GD_TILE_M0(tile) ((((tile) / n_tiles) * CL + cta_rank) * BLOCK_M)
@@ -333,13 +339,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (CL == 1) {
                         mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                         int a_col = kb * BLOCK_K, a_row = m0;
-                        if (MODE == MODE_CONV) {  // tap-shifted pixel rows; rows outside [0, M) are zero-filled by TMA
+                        if (IS_CONV) {  // tap-shifted pixel rows; rows outside [0, M) are zero-filled by TMA
                             const int tap = kb / p.kb_per_tap;
-                            a_col = ((kb - tap * p.kb_per_tap) * BLOCK_K) % p.a_cols;  // wraps: split rows are walked hi, lo, hi
+                            a_col = (kb - tap * p.kb_per_tap) * BLOCK_K;
+                            if (MODE == MODE_CONV) a_col %= p.a_cols;  // wraps: split rows are walked hi, lo, hi
                             a_row = m0 + p.tap_shift[tap];
                         }
-                        tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_a, &full_bar[stage], a_col, a_row);
-                        tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmap_b, &full_bar[stage], kb * BLOCK_K, n0);
+                        tma_load_2d(smem_a + stage * NA * Cfg::A_BYTES, &tmap_a, &full_bar[stage], a_col, a_row);
+                        if (NA == 2)  // the lo plane of the same 64 channels
+                            tma_load_2d(smem_a + (stage * NA + 1) * Cfg::A_BYTES, &tmap_a, &full_bar[stage], a_col + (p.a_cols >> 1), a_row);
+#pragma unroll
+                        for (int b = 0; b < NB; ++b)
+                            tma_load_2d(smem_b + (stage * NB + b) * Cfg::B_BYTES, &tmap_b, &full_bar[stage], (kb * NB + b) * BLOCK_K, n0);
                     } else {
                         // both CTAs fill their own slot; all bytes are counted on the leader's barrier
                         if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], CL * Cfg::STAGE_BYTES);
@@ -370,6 +381,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after_sync();
+                    if constexpr (NB == 2) {
+                        // operand reuse: every (A, B) product of the stage from tiles that were loaded once
+                        constexpr int NPAIR = NA + 1;  // S1: (A,B0) (A,B1);  S2: (hi,Whi) (lo,Whi) (hi,Wlo)
+#pragma unroll
+                        for (int pr = 0; pr < NPAIR; ++pr) {
+                            const int ai = (NA == 2 && pr == 1) ? 1 : 0, bi = (pr == NPAIR - 1) ? 1 : 0;
+                            const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + (stage * NA + ai) * Cfg::A_BYTES));
+                            const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + (stage * NB + bi) * Cfg::B_BYTES));
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                                umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | pr | k) != 0 ? 1u : 0u);
+                        }
+                    } else {
                     const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::A_BYTES));
                     const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::B_BYTES));
 #pragma unroll
@@ -379,6 +403,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                         else
                             umma_bf16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
                     }
                     // frees the smem slot (of both CTAs of a pair) when these MMAs retire
                     if (CL == 1)
@@ -442,7 +467,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             };
             bool conv_keep = false;
             size_t conv_out_row = 0;
-            if (MODE == MODE_CONV) {  // pixel row -> (image, y, x); only pixels inside the window (and on the stride) are stored
+            if (IS_CONV) {  // pixel row -> (image, y, x); only pixels inside the window (and on the stride) are stored
                 const int gsz = p.grid_h * p.grid_w;
                 const int img = row / gsz;
                 const int rem = row - img * gsz;
@@ -567,7 +592,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             tma_store_2d(&tmap_out, stg, col0, row0);
                         bulk_commit_group();
                     }
-                } else if (MODE == MODE_CONV) {
+                } else if (IS_CONV) {
                     tmem_ld_wait();
                     if (c == WCOLS / 32 - 1) release_accumulator();
                     if (conv_keep && col0 < p.c_store) epilogue_conv_chunk(p, conv_out_row, col0, v);
@@ -669,7 +694,7 @@ template <int BN, int MODE>
 static int launch_gemm(const GemmParams& p, const void* A, int lda, const void* W, int ldw, cudaStream_t stream) {
     const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
     const int policy = cta_pair_policy();
-    if (BN >= 128 && MODE != MODE_DDPM && MODE != MODE_DIRECT && MODE != MODE_CONV && policy > 0 && (p.K >= 1024 || policy == 2) &&
+    if (BN >= 128 && MODE != MODE_DDPM && MODE != MODE_DIRECT && MODE < MODE_CONV && policy > 0 && (p.K >= 1024 || policy == 2) &&
         ((m_tiles + 1) / 2) * (p.N / BN) >= sm_count() / 2)
         return launch_gemm_cl<BN, MODE, 2>(p, A, lda, W, ldw, stream);
     return launch_gemm_cl<BN, MODE, 1>(p, A, lda, W, ldw, stream);
@@ -677,9 +702,9 @@ static int launch_gemm(const GemmParams& p, const void* A, int lda, const void* 
 
 // MODE_CONV: the A operand is the pixel-row tensor [rows, c_in]; every tap reads the same columns at shifted rows, and
 // W is [c_out, n_taps * c_in] with the taps along K.
-template <int BN>
+template <int BN, int MODE>
 static int launch_conv(const GemmParams& p, const void* A, int c_in, const void* W, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN, 1>;
+    using Cfg = GemmCfg<BN, 1, (MODE == MODE_CONV_S2) ? 2 : 1, (MODE >= MODE_CONV_S1) ? 2 : 1>;
     CUtensorMap ta, tb;
     int rc = make_tmap_2d_bf16(&ta, A, p.M, c_in, c_in, BLOCK_M);
     if (rc) return rc;
@@ -687,13 +712,13 @@ static int launch_conv(const GemmParams& p, const void* A, int c_in, const void*
     if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        GD_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, MODE_CONV, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GD_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::SMEM_BYTES));
         attr_set = true;
     }
     const int work = ((p.M + BLOCK_M - 1) / BLOCK_M) * (p.N / BN);
     const int grid = work < sm_count() ? work : sm_count();
-    GD_CUDA_CHECK(launch_k(gemm_bf16_tn_kernel<BN, MODE_CONV, 1>, grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream, 1, ta, tb, ta, p));
+    GD_CUDA_CHECK(launch_k(gemm_bf16_tn_kernel<BN, MODE, 1>, grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream, 1, ta, tb, ta, p));
     count_launch();
     GD_CUDA_CHECK(cudaGetLastError());
     return GD_OK;
@@ -787,6 +812,9 @@ extern "C" int gd_conv_taps_bf16(const gd_conv_desc* d, void* stream) {
     if (d->in_ld <= 0 || d->in_ld % BLOCK_K || d->k_per_tap <= 0 || d->k_per_tap % BLOCK_K || d->c_out <= 0 || d->c_out % 64)
         return set_error(GD_ERR_INVALID, "gd_conv_taps_bf16: in_ld=%d / k_per_tap=%d / c_out=%d must be multiples of 64", d->in_ld,
                          d->k_per_tap, d->c_out);
+    if (d->walk < 0 || d->walk > 2 || (d->walk == 1 && (d->in_ld != 64 || d->k_per_tap != 128)) ||
+        (d->walk == 2 && (d->in_ld % 128 || d->k_per_tap != d->in_ld)))
+        return set_error(GD_ERR_INVALID, "gd_conv_taps_bf16: walk=%d does not fit in_ld=%d / k_per_tap=%d", d->walk, d->in_ld, d->k_per_tap);
     if (d->c_store <= 0 || d->c_store % 32 || d->c_store > d->c_out)
         return set_error(GD_ERR_INVALID, "gd_conv_taps_bf16: c_store=%d must be a multiple of 32 and <= c_out", d->c_store);
     if (d->n_taps < 1 || d->n_taps > GD_CONV_MAX_TAPS) return set_error(GD_ERR_INVALID, "gd_conv_taps_bf16: n_taps out of range");
@@ -804,7 +832,7 @@ extern "C" int gd_conv_taps_bf16(const gd_conv_desc* d, void* stream) {
     GemmParams p{};
     p.M = (int)rows, p.N = d->c_out, p.K = d->n_taps * d->k_per_tap;
     p.bias = d->bias, p.scale = d->scale, p.shift = d->shift, p.relu = d->relu;
-    p.kb_per_tap = d->k_per_tap / BLOCK_K, p.a_cols = d->in_ld;
+    p.kb_per_tap = d->k_per_tap / (BLOCK_K * (d->walk ? 2 : 1)), p.a_cols = d->in_ld;  // pipeline stages per tap
     p.split_out = d->split_out, p.c_store = d->c_store;
     for (int t = 0; t < d->n_taps; ++t) p.tap_shift[t] = d->tap_shift[t];
     p.grid_h = d->grid_h, p.grid_w = d->grid_w;
@@ -814,9 +842,18 @@ extern "C" int gd_conv_taps_bf16(const gd_conv_desc* d, void* stream) {
     p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(d->out), p.ldo_bf16 = d->out_ld;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
-    const int bn = (d->c_out % 256 == 0 && m_tiles * (d->c_out / 256) >= sm_count()) ? 256
+    // operand-reuse stages hold up to four tiles, so those kernels stop at 128-wide tiles (>= 3 stages in 227 KB)
+    const int bn = (d->walk == 0 && d->c_out % 256 == 0 && m_tiles * (d->c_out / 256) >= sm_count()) ? 256
                    : (d->c_out % 128 == 0 && m_tiles * (d->c_out / 128) >= sm_count()) ? 128 : 64;
-    if (bn == 256) return launch_conv<256>(p, d->in, d->in_ld, d->W, s);
-    if (bn == 128) return launch_conv<128>(p, d->in, d->in_ld, d->W, s);
-    return launch_conv<64>(p, d->in, d->in_ld, d->W, s);
+    if (d->walk == 1) {
+        if (bn == 128) return launch_conv<128, MODE_CONV_S1>(p, d->in, d->in_ld, d->W, s);
+        return launch_conv<64, MODE_CONV_S1>(p, d->in, d->in_ld, d->W, s);
+    }
+    if (d->walk == 2) {
+        if (bn == 128) return launch_conv<128, MODE_CONV_S2>(p, d->in, d->in_ld, d->W, s);
+        return launch_conv<64, MODE_CONV_S2>(p, d->in, d->in_ld, d->W, s);
+    }
+    if (bn == 256) return launch_conv<256, MODE_CONV>(p, d->in, d->in_ld, d->W, s);
+    if (bn == 128) return launch_conv<128, MODE_CONV>(p, d->in, d->in_ld, d->W, s);
+    return launch_conv<64, MODE_CONV>(p, d->in, d->in_ld, d->W, s);
 }

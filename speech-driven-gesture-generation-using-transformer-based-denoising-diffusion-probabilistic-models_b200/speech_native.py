@@ -55,7 +55,7 @@ def _pad_vec(v, c_pad):
     return out
 
 
-def _pack_conv(weight, c_in, co_pad, split):
+def _pack_conv(weight, c_in, co_pad, split, reuse=True):
     """(Co, Ci, kh, kw) -> bf16 [co_pad, kh*kw*k_per_tap]: taps (ky, kx) row-major along K, then the K walk of one tap over an
     input row of `c_in` stored channels.  Plain rows: k = channel.  Split rows [hi(c_in) | lo(c_in)]: the walk wraps around
     the row; the first pass multiplies both planes by Whi, the second pass multiplies the hi plane by Wlo (bf16x3)."""
@@ -64,15 +64,21 @@ def _pack_conv(weight, c_in, co_pad, split):
     w = th.zeros(co_pad, taps, c_in, dtype=th.float32, device=weight.device)
     w[:co, :, :ci] = weight.float().permute(0, 2, 3, 1).reshape(co, taps, ci)
     if not split:
-        return w.reshape(co_pad, taps * c_in).to(th.bfloat16).contiguous(), c_in
+        return w.reshape(co_pad, taps * c_in).to(th.bfloat16).contiguous(), c_in, 0
     whi = w.to(th.bfloat16).float()
     wlo = (w - whi).to(th.bfloat16).float()
+    if reuse and c_in % 64 == 0:
+        # walk 2: per tap and 64-channel block [Whi(64) | Wlo(64)] - the kernel loads the hi and lo input tiles of the block
+        # once and forms hi*Whi + lo*Whi + hi*Wlo from them
+        blocks = th.stack([whi.reshape(co_pad, taps, c_in // 64, 64), wlo.reshape(co_pad, taps, c_in // 64, 64)], dim=3)
+        return blocks.reshape(co_pad, taps * 2 * c_in).to(th.bfloat16).contiguous(), 2 * c_in, 2
     in_ld, k_per_tap = 2 * c_in, _pad_to(3 * c_in)
     k = th.arange(k_per_tap, device=weight.device)
     col, second = k % in_ld, k >= in_ld
     ch, lo_plane = col % c_in, col >= c_in
     out = th.where(second[None, None, :], th.where(lo_plane[None, None, :], wlo.new_zeros(()), wlo[:, :, ch]), whi[:, :, ch])
-    return out.reshape(co_pad, taps * k_per_tap).to(th.bfloat16).contiguous(), k_per_tap
+    # c_in == 32: the packing is already [Whi|Whi | Wlo|0] per tap; walk 1 lets the kernel load the input tile once
+    return out.reshape(co_pad, taps * k_per_tap).to(th.bfloat16).contiguous(), k_per_tap, (1 if reuse and c_in == 32 else 0)
 
 
 class _Conv:
@@ -84,7 +90,7 @@ class _Conv:
         self.c_store = _pad_to(conv.out_channels, 32) if split else self.c_out
         self.in_ld = 2 * c_in if split else c_in
         self.out_ld = 2 * self.c_store if split else self.c_store
-        self.w, self.k_per_tap = _pack_conv(conv.weight.detach(), c_in, self.c_out, split)
+        self.w, self.k_per_tap, self.walk = _pack_conv(conv.weight.detach(), c_in, self.c_out, split)
         self.bias = _pad_vec(conv.bias.detach() if conv.bias is not None else None, self.c_out)
         self.scale, self.shift = _fold_bn(bn, self.c_out)
         self.relu = int(relu)
@@ -213,7 +219,7 @@ class NativeSpeechEncoder:
         d.stride = stride
         d.out, d.out_ld = _p(dst), cv.out_ld
         d.out_img_stride, d.out_y_stride, d.out_x_stride, d.out_offset = out_strides
-        d.c_store, d.split_out = cv.c_store, cv.split
+        d.c_store, d.split_out, d.walk = cv.c_store, cv.split, cv.walk
         gd.check(self.lib.gd_conv_taps_bf16(C.byref(d), self.L.stream()), "gd_conv_taps_bf16")
 
     def _same_conv(self, cv, src, n, src_hw, dst, dst_hw):

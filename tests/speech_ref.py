@@ -26,19 +26,27 @@ def put(out, index, v, c, split):
 
 
 def conv_taps_ref(inp, W, n_images, grid_h, grid_w, taps, k_per_tap, bias, scale, shift, relu, window, stride, out, out_strides,
-                  c_store, split_out):
+                  c_store, split_out, walk=0):
     """gd_conv_taps_bf16 on tensors: inp [rows, in_ld], W [c_out, n_taps*k_per_tap], out [*, out_ld] modified in place."""
     rows, in_ld = n_images * grid_h * grid_w, inp.shape[1]
     A = inp[:rows].float()
     Wf = W.float()
-    walk = th.arange(k_per_tap, device=inp.device) % in_ld
+    if walk == 2:   # per 64-channel block the W columns are [Whi(64) | Wlo(64)]; input columns hi, lo, hi
+        c = in_ld // 2
+        blk = th.arange(c // 64, device=inp.device)[:, None] * 64 + th.arange(64, device=inp.device)[None]   # [blocks, 64]
+        cols = th.cat([blk, blk + c, blk], dim=1).reshape(-1)                  # input column per product term
+        wbase = (th.arange(c // 64, device=inp.device)[:, None] * 128 + th.arange(64, device=inp.device)[None])
+        wcols = th.cat([wbase, wbase, wbase + 64], dim=1).reshape(-1)
+    else:           # generic (and walk 1, which is the same arithmetic): k-th element reads column k mod in_ld
+        cols = th.arange(k_per_tap, device=inp.device) % in_ld
+        wcols = th.arange(k_per_tap, device=inp.device)
     acc = th.zeros(rows, W.shape[0], dtype=th.float32, device=inp.device)
     for t, sh in enumerate(taps):
         shifted = th.zeros_like(A)
         lo, hi = max(0, -sh), min(rows, rows - sh)
         if hi > lo:
             shifted[lo:hi] = A[lo + sh:hi + sh]
-        acc += shifted[:, walk] @ Wf[:, t * k_per_tap:(t + 1) * k_per_tap].T
+        acc += shifted[:, cols] @ Wf[:, t * k_per_tap + wcols].T
     if bias is not None:
         acc = acc + bias
     if relu:
@@ -150,7 +158,7 @@ class FakeLauncher:
         out2 = out.view(-1, d.out_ld)
         conv_taps_ref(inp, W, d.n_images, d.grid_h, d.grid_w, [d.tap_shift[i] for i in range(d.n_taps)], d.k_per_tap,
                       self._t(d.bias), self._t(d.scale), self._t(d.shift), d.relu, (d.y0, d.y1, d.x0, d.x1), d.stride, out2,
-                      (d.out_img_stride, d.out_y_stride, d.out_x_stride, d.out_offset), d.c_store, d.split_out)
+                      (d.out_img_stride, d.out_y_stride, d.out_x_stride, d.out_offset), d.c_store, d.split_out, d.walk)
         return 0
 
     def gd_speech_stem(self, mel, w, b, sc, sh, out, n, H, W, c_real, c_pad, split, stream):

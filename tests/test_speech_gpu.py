@@ -16,11 +16,11 @@ def _stream():
     return th.cuda.current_stream().cuda_stream
 
 
-def _conv(gd, inp, W, n, gh, gw, taps, bias, scale, shift, relu, window, stride, out, out_strides, split=0, c_store=None):
+def _conv(gd, inp, W, n, gh, gw, taps, bias, scale, shift, relu, window, stride, out, out_strides, split=0, c_store=None, walk=0):
     d = gd.ConvDesc()
     d.inp, d.W, d.n_images, d.grid_h, d.grid_w = inp.data_ptr(), W.data_ptr(), n, gh, gw
     d.in_ld, d.k_per_tap, d.c_out, d.n_taps = inp.shape[1], W.shape[1] // len(taps), W.shape[0], len(taps)
-    d.c_store, d.split_out = c_store or W.shape[0], split
+    d.c_store, d.split_out, d.walk = c_store or W.shape[0], split, walk
     for i, t in enumerate(taps):
         d.tap_shift[i] = t
     d.bias, d.scale, d.shift, d.relu = gd.ptr(bias), scale.data_ptr(), shift.data_ptr(), int(relu)
@@ -87,14 +87,16 @@ def test_conv_taps_same_padding(gd, n, H, W, ci, co, k, stride, relu, with_bias)
     (70, 32, 16, 128, 128, 3, 1, False),
     (40, 16, 8, 256, 256, 3, 1, True),   # K = 9 * 768
 ])
-def test_conv_taps_split_precision(gd, n, H, W, ci, co, k, stride, relu):
+@pytest.mark.parametrize("reuse", [True, False])
+def test_conv_taps_split_precision(gd, n, H, W, ci, co, k, stride, relu, reuse):
     """bf16x3: split feature maps and split weights reproduce the fp32 convolution to ~1e-5 relative."""
     from gesture_b200.speech_native import _pack_conv, _pad_to
     g = th.Generator(device="cuda").manual_seed(n * 100 + ci + co + k + 1)
     x = _bordered(n, H, W, ci, g, split=1)
     w4 = th.randn(co, ci, k, k, device="cuda", generator=g) / math.sqrt(ci * k * k)
     co_pad = _pad_to(co)
-    Wp, kpt = _pack_conv(w4, ci, co_pad, 1)
+    Wp, kpt, walk = _pack_conv(w4, ci, co_pad, 1, reuse)
+    assert walk == (0 if not reuse else 1 if ci == 32 else 2)
     pad = lambda v: th.cat([v, v.new_zeros(co_pad - co)])  # noqa: E731
     scale, shift = pad(th.rand(co, device="cuda", generator=g) + 0.5), pad(th.randn(co, device="cuda", generator=g) * 0.1)
     Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
@@ -102,7 +104,7 @@ def test_conv_taps_split_precision(gd, n, H, W, ci, co, k, stride, relu):
     taps = [0] if k == 1 else [(ky - 1) * gw + (kx - 1) for ky in range(3) for kx in range(3)]
     geo = ((Ho + 2) * (Wo + 2), Wo + 2, 1, Wo + 3)
     out = th.zeros(n * (Ho + 2) * (Wo + 2), 2 * co, device="cuda", dtype=th.bfloat16)
-    _conv(gd, x, Wp, n, H + 2, gw, taps, None, scale, shift, relu, (1, H, 1, W), stride, out, geo, split=1, c_store=co)
+    _conv(gd, x, Wp, n, H + 2, gw, taps, None, scale, shift, relu, (1, H, 1, W), stride, out, geo, split=1, c_store=co, walk=walk)
     xv = ref.join(x, ci, 1).view(n, H + 2, W + 2, ci)[:, 1:-1, 1:-1].permute(0, 3, 1, 2).double()
     y = th.nn.functional.conv2d(xv, w4.double(), None, stride=stride, padding=k // 2)
     y = (y.clamp_min(0) if relu else y) * scale[None, :co, None, None] + shift[None, :co, None, None]
@@ -142,6 +144,8 @@ def test_conv_taps_rejects_bad_arguments(gd):
         _conv(gd, x, w, 1, 10, 10, [0], None, v, v, False, (1, 8, 1, 8), 3, x, (100, 10, 1, 11))   # stride 3
     with pytest.raises(gd.GdError):
         _conv(gd, x, w, 1, 10, 10, [0], None, v, v, False, (1, 8, 1, 8), 1, x, (100, 10, 1, 11), c_store=48)
+    with pytest.raises(gd.GdError):
+        _conv(gd, x, w, 1, 10, 10, [0], None, v, v, False, (1, 8, 1, 8), 1, x, (100, 10, 1, 11), walk=2)  # in_ld 64 is not 2c
 
 
 @pytest.mark.parametrize("split", [0, 1])
