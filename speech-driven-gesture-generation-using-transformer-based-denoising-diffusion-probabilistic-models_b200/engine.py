@@ -222,7 +222,7 @@ class SamplingChain:
         self.speech_impl = "torch" if self.f32act else env("GD_SPEECH", getattr(model, "speech_impl", "native"))
         if self.speech_impl not in ("native", "native-bf16", "torch"):
             raise ValueError(f"speech_impl must be 'native', 'native-bf16' or 'torch', got {self.speech_impl!r}")
-        self.native_encoder_chunk = getattr(model, "native_encoder_chunk", 64)
+        self.native_encoder_chunk = int(env("GD_SPEECH_CHUNK", getattr(model, "native_encoder_chunk", 128)))
         self.graph = None
         self._plan_key = None
         self.Tm = None
