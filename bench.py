@@ -359,6 +359,8 @@ def run_b200(args):
                        "l2_policy": "inputs_larger_than_L2 (per-step activations + 1000-step noise tape >> 126 MB)",
                        "parallelism": f"clip-sharded x{world}, all_gather of poses"},
             "ms_per_denoise_step": ms_replay / n_steps, "chain_replay_ms": ms_replay,
+            # per chain, outside the 1000 replays: speech encoder + conditioning GEMMs + on-device noise tape
+            "chain_begin_ms": ms_per_chain - ms_replay, "speech_encoder": chain.speech_impl,
             "step_flops_executed": total_flops,
             "model_tflops_chain": total_flops * n_steps / (ms_replay * 1e-3) / 1e12,
             "clocks": clk.summary(), "e2e": e2e,

@@ -47,7 +47,8 @@ def main():
         th.cuda.synchronize()
         print("ok")
         return
-    row = {"workload": args.workload, "clips": clips, "encoder_chunk": chain.encoder_chunk}
+    row = {"workload": args.workload, "clips": clips, "speech_impl": chain.speech_impl,
+           "encoder_chunk": chain.encoder_chunk if chain.speech_impl == "torch" else chain.native_encoder_chunk}
     row["begin_ms"] = timed(lambda: chain.begin(x_T, wav))
     row["begin_no_tape_ms"] = timed(lambda: chain.begin(x_T, wav, need_tape=False))
     row["speech_encoder_ms"] = timed(lambda: chain._speech_features(wav))

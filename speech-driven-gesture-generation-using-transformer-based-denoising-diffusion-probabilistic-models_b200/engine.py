@@ -182,7 +182,7 @@ class SamplingChain:
     """One (model, diffusion, batch shape, algorithm) sampling context: buffers + plan + captured graph."""
 
     def __init__(self, model, diffusion, shape, alg, device, precision="bf16", graph_steps=1, use_graph=True,
-                 fuse_ln=False):
+                 fuse_ln=False, speech_impl="native"):
         if device.type != "cuda":
             raise gd.GdError("the DDPM sampling path runs only on a CUDA device (sm_100a); there is no CPU fallback")
         self.model, self.diffusion, self.alg = model, diffusion, alg
@@ -219,7 +219,7 @@ class SamplingChain:
         # once-per-clip speech encoder: "native" = ResNetSE-34 on our tensor-core convolutions in split precision (bf16x3:
         # fp32-class products), "native-bf16" = the same with plain bf16 feature maps (faster, ~1e-2 feature error that a
         # random-weight ResNet amplifies), "torch" = the fp32 nn.Module through cuDNN (the fp32-activation parity path)
-        self.speech_impl = "torch" if self.f32act else env("GD_SPEECH", getattr(model, "speech_impl", "native"))
+        self.speech_impl = "torch" if self.f32act else env("GD_SPEECH", speech_impl)
         if self.speech_impl not in ("native", "native-bf16", "torch"):
             raise ValueError(f"speech_impl must be 'native', 'native-bf16' or 'torch', got {self.speech_impl!r}")
         self.native_encoder_chunk = int(env("GD_SPEECH_CHUNK", getattr(model, "native_encoder_chunk", 128)))
@@ -613,7 +613,8 @@ def chain_for(model, diffusion, shape, alg, device, **kw):
     if device.type == "cuda" and device.index is None:
         device = th.device("cuda", th.cuda.current_device())
     opts = dict(precision=getattr(model, "precision", "bf16"), graph_steps=getattr(model, "graph_steps", 0),
-                use_graph=getattr(model, "use_graph", True), fuse_ln=getattr(model, "fuse_layernorm", False))
+                use_graph=getattr(model, "use_graph", True), fuse_ln=getattr(model, "fuse_layernorm", False),
+                speech_impl=getattr(model, "speech_impl", "native"))
     opts.update(kw)
     key = (id(model), id(diffusion), shape, alg, str(device), model.weights_version, tuple(sorted(opts.items())))
     ch = _CHAINS.get(key)

@@ -1,4 +1,6 @@
 """CUDA sampling path vs the CPU oracle on freshly seeded inputs (small N: the oracle finishes in seconds)."""
+import os
+
 import pytest
 import torch as th
 
@@ -172,3 +174,37 @@ def test_batch_invariance():
     part = gen.generate_sample((2, C, T), wav[3:], noise=x_T[3:], sample_alg="ddpm", device="cuda", progress=False,
                                noise_tape=tape[:, 3:])
     assert th.equal(full[3:], part)
+
+
+def test_speech_encoder_implementations_agree():
+    """The chain's conditioning through the three encoder implementations: native split precision (default), native plain
+    bf16, and the fp32 torch module.  With the boosted weights (a random 34-convolution ResNet amplifies rounding noise)
+    split precision stays at the bf16 rounding of the final features; plain bf16 does not."""
+    from gesture_b200.engine import chain_for
+    model, diffusion, C, T, L, _ = build("beat", "boost", device="cuda")
+    N = 5
+    wav = synthetic_wav(N, L, seed=21).cuda()
+    feats = {}
+    for impl in ("native", "native-bf16", "torch"):
+        model.speech_impl = impl
+        chain = chain_for(model, diffusion, (N, C, T), "ddpm", "cuda", use_graph=False)
+        assert chain.speech_impl == impl or os.environ.get("GD_SPEECH")
+        feats[impl] = [f.clone() for f in chain._speech_features(wav)]
+    del model.speech_impl
+    for a, b, c in zip(feats["native"], feats["native-bf16"], feats["torch"]):
+        assert a.shape == c.shape and tuple(a.shape[::2]) == (N, model.speech_encoder.wav_proj_layer.out_features)
+        assert rel_l2(a, c) < 4e-3, rel_l2(a, c)
+        assert rel_l2(b, c) < 0.2
+        assert rel_l2(a, c) < rel_l2(b, c)
+
+
+def test_eval_infer_time_ddim():
+    """Generator.eval_infer_time_ddim / gpu_warm_up_ddim (generator.py:16-78) on a 10-step respaced process."""
+    from gesture_b200.generator import Generator
+    model, diffusion, C, T, L, _ = build("beat", "boost", respacing="ddim10", device="cuda")
+    N = 3
+    kw = {"wav": synthetic_wav(N, L, seed=2).cuda()}
+    gen = Generator(model, diffusion)
+    for alg in ("ddim", "ddpm"):
+        mean_ms, std_ms = gen.eval_infer_time_ddim((N, C, T), kw, sample_alg=alg, repetitions=3, device="cuda")
+        assert 0 < mean_ms < 5e3 and std_ms >= 0
