@@ -80,3 +80,35 @@ def test_head_merge_is_fc_then_projection():
     mine[:, :, :32] = feat.permute(0, 2, 1)          # our [y][c] layout, channels padded to 64
     out = mine.reshape(5, -1) @ hd.w.float().T + hd.b
     assert ((ref - out).norm() / ref.norm()).item() < 5e-3  # bf16 merged weight
+
+
+@pytest.mark.parametrize("ci,co,k", [(32, 32, 3), (32, 64, 1), (64, 64, 3), (128, 64, 3)])
+def test_split_weight_packings_agree(ci, co, k):
+    """The three K layouts of a split-precision convolution (generic wrap walk, walk 1 / walk 2 with operand reuse) are the
+    same arithmetic: hi*Whi + lo*Whi + hi*Wlo, which matches the float64 convolution to ~1e-5."""
+    from speech_ref import conv_taps_ref, join
+    g = th.Generator().manual_seed(ci + co + k)
+    n, H, W = 2, 6, 5
+    x = th.zeros(n, H + 2, W + 2, ci)
+    x[:, 1:-1, 1:-1] = th.randn(n, H, W, ci, generator=g)
+    x = x.reshape(-1, ci)
+    hi = x.to(th.bfloat16)
+    rows = th.cat([hi, (x - hi.float()).to(th.bfloat16)], dim=1).float()
+    w4 = th.randn(co, ci, k, k, generator=g) / (ci * k * k) ** 0.5
+    co_pad = speech_native._pad_to(co)
+    gw = W + 2
+    taps = [0] if k == 1 else [(ky - 1) * gw + (kx - 1) for ky in range(3) for kx in range(3)]
+    scale, shift = th.ones(co_pad), th.zeros(co_pad)
+    outs = []
+    for reuse in (False, True):
+        Wp, kpt, walk = speech_native._pack_conv(w4, ci, co_pad, 1, reuse)
+        assert walk == (0 if not reuse else 1 if ci == 32 else 2) and Wp.shape == (co_pad, len(taps) * kpt)
+        out = th.zeros(n * (H + 2) * gw, 2 * co)
+        conv_taps_ref(rows, Wp, n, H + 2, gw, taps, kpt, None, scale, shift, 0, (1, H, 1, W), 1, out,
+                      ((H + 2) * gw, gw, 1, gw + 1), co, 1, walk)
+        outs.append(join(out, co, 1).view(n, H + 2, gw, co)[:, 1:-1, 1:-1])
+    want = th.nn.functional.conv2d(join(rows, ci, 1).view(n, H + 2, gw, ci)[:, 1:-1, 1:-1].permute(0, 3, 1, 2).double(),
+                                   w4.double(), padding=k // 2).permute(0, 2, 3, 1)
+    for o in outs:
+        assert ((o.double() - want).norm() / want.norm()).item() < 3e-5
+    assert ((outs[0] - outs[1]).norm() / outs[0].norm()).item() < 1e-5  # same products, different fp32 summation order
