@@ -263,3 +263,19 @@ def test_mel_front_end(gd, n, wav_len):
         # the un-normalised mel powers, checked through the reference statement used on CPU
         raw2 = ref.mel_power_ref(wav, native.window, native.fb, native.preemph, 1e-6)
         assert ((raw2 - raw).norm() / raw.norm()).item() < 1e-5
+
+
+@pytest.mark.parametrize("name", ["beat", "tedexp"])
+def test_native_encoder_against_reference_golden_features(gd, name):
+    """The CUDA encoder against the features the unmodified reference produced (tests/golden/*.npz)."""
+    from gesture_b200.engine import _Launcher
+    from gesture_b200.speech_native import NativeSpeechEncoder
+    from util import build, load_golden, rel_l2, synthetic_wav
+    g = load_golden(name)
+    for weights in ("init", "boost"):
+        model, _, _, _, L, _ = build(name, weights, device="cuda")
+        native = NativeSpeechEncoder(model.speech_encoder, _Launcher(), th.device("cuda", 0))
+        out = native(synthetic_wav(2, L, seed=123).cuda())
+        for nm, f in zip(("low", "mid", "high"), out):
+            err = rel_l2(f, g[f"{weights}.feat_{nm}"])
+            assert err < 4e-3, (name, weights, nm, err)

@@ -112,3 +112,19 @@ def test_split_weight_packings_agree(ci, co, k):
     for o in outs:
         assert ((o.double() - want).norm() / want.norm()).item() < 3e-5
     assert ((outs[0] - outs[1]).norm() / outs[0].norm()).item() < 1e-5  # same products, different fp32 summation order
+
+
+@pytest.mark.parametrize("name", ["beat", "tedexp"])
+def test_native_plan_against_reference_golden_features(monkeypatch, name):
+    """Pinned to the real reference: the golden speech features were written by the unmodified HA2GSpeechEncoder
+    (tests/golden/make_golden.py) on the same weights and synthetic wav."""
+    from util import build, load_golden, rel_l2, synthetic_wav
+    g = load_golden(name)
+    for weights in ("init", "boost"):
+        model, _, _, _, L, _ = build(name, weights)
+        fake = FakeLauncher()
+        monkeypatch.setattr(speech_native, "_p", fake.track)
+        native = speech_native.NativeSpeechEncoder(model.speech_encoder, fake, th.device("cpu"))
+        out = native(synthetic_wav(2, L, seed=123))
+        for nm, f in zip(("low", "mid", "high"), out):
+            assert rel_l2(f, g[f"{weights}.feat_{nm}"]) < 4e-3, (name, weights, nm, rel_l2(f, g[f"{weights}.feat_{nm}"]))
