@@ -166,7 +166,8 @@ class NativeSpeechEncoder:
         """Buffers of the mel kernel: the module's own Hann window and filterbank (state_dict buffers), float64 twiddles,
         and the non-zero band of every mel filter."""
         pre, ms = self.enc.wav2spec[0], self.enc.wav2spec[1]
-        assert ms.spectrogram.n_fft == 1024 and ms.spectrogram.hop == 512, "the mel kernel is built for n_fft 1024 / hop 512"
+        hop = getattr(ms.spectrogram, "hop", None) or ms.spectrogram.hop_length  # ours / torchaudio's attribute name
+        assert ms.spectrogram.n_fft == 1024 and hop == 512, "the mel kernel is built for n_fft 1024 / hop 512"
         self.window = ms.spectrogram.window.detach().float().contiguous()
         self.fb = ms.mel_scale.fb.detach().float().contiguous()
         assert tuple(self.fb.shape) == (513, 128)
