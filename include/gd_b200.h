@@ -298,7 +298,8 @@ int gd_speech_stem(const float* mel, const float* w, const float* bias, const fl
  * w1 fp32 [c_hidden, c_real], w2 fp32 [c_real, c_hidden]; gate fp32 [n_images, c] (padding channels get 0).
  * The pixel sum is taken in fixed slices that depend on the grid only: the gate of a clip does not depend on the batch
  * it is in.  `scratch`: at least gd_se_gate_scratch_bytes() bytes, zeroed once by the caller (the kernel leaves its
- * counters at zero), not shared with a concurrently running gd_se_gate. */
+ * counters at zero; they sit in a fixed-size block at the start, so one scratch sized for the largest batch serves calls
+ * with any smaller n_images), not shared with a concurrently running gd_se_gate. */
 int64_t gd_se_gate_scratch_bytes(int32_t n_images, int32_t grid_h, int32_t grid_w, int32_t c);
 int gd_se_gate(const void* y_bf16, int32_t n_images, int32_t grid_h, int32_t grid_w, int32_t c, int32_t split, int32_t c_real,
                int32_t c_hidden, const float* w1, const float* b1, const float* w2, const float* b2, float* gate,

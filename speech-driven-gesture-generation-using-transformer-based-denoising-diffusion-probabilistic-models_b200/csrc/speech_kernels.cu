@@ -251,9 +251,13 @@ extern "C" int gd_speech_stem(const float* mel, const float* w, const float* bia
     return GD_OK;
 }
 
+// scratch = [SE_MAX_IMAGES arrival counters | per-image partial sums].  The counter block has a fixed size so that calls with
+// different image counts on the same scratch agree on where the (self-resetting) counters live.
+constexpr int SE_MAX_IMAGES = 65536;
+
 extern "C" int64_t gd_se_gate_scratch_bytes(int32_t n_images, int32_t grid_h, int32_t grid_w, int32_t c) {
     const int64_t slices = ((int64_t)grid_h * grid_w + SE_SLICE - 1) / SE_SLICE;
-    return 4 * (((int64_t)n_images + 3) / 4 * 4 + (int64_t)n_images * slices * c);
+    return 4 * ((int64_t)SE_MAX_IMAGES + (int64_t)n_images * slices * c);
 }
 
 extern "C" int gd_se_gate(const void* y_bf16, int32_t n_images, int32_t grid_h, int32_t grid_w, int32_t c, int32_t split,
@@ -268,7 +272,7 @@ extern "C" int gd_se_gate(const void* y_bf16, int32_t n_images, int32_t grid_h, 
         return set_error(GD_ERR_INVALID, "gd_se_gate: scratch too small (see gd_se_gate_scratch_bytes)");
     if (n_images > 65535) return set_error(GD_ERR_INVALID, "gd_se_gate: at most 65535 images per launch");
     int* counters = reinterpret_cast<int*>(scratch);
-    float* partial = reinterpret_cast<float*>(scratch) + ((n_images + 3) & ~3);
+    float* partial = reinterpret_cast<float*>(scratch) + SE_MAX_IMAGES;
     GD_CUDA_CHECK(launch_k(se_gate_kernel, dim3(slices, n_images), 256, 0, reinterpret_cast<cudaStream_t>(stream), 1,
                            reinterpret_cast<const __nv_bfloat16*>(y_bf16), grid_h * grid_w, (grid_h - 2) * (grid_w - 2), c,
                            split, c_real, c_hidden, w1, b1, w2, b2, gate, partial, counters));

@@ -168,7 +168,7 @@ class FakeLauncher:
 
     @staticmethod
     def gd_se_gate_scratch_bytes(n, gh, gw, c):
-        return 4 * ((n + 3) // 4 * 4 + n * ((gh * gw + 255) // 256) * c)
+        return 4 * (65536 + n * ((gh * gw + 255) // 256) * c)
 
     def gd_se_gate(self, y, n, gh, gw, c, split, c_real, c_hidden, w1, b1, w2, b2, gate, scratch, scratch_bytes, stream):
         self.calls.append("gd_se_gate")

@@ -279,3 +279,21 @@ def test_native_encoder_against_reference_golden_features(gd, name):
         for nm, f in zip(("low", "mid", "high"), out):
             err = rel_l2(f, g[f"{weights}.feat_{nm}"])
             assert err < 4e-3, (name, weights, nm, err)
+
+
+def test_workspace_survives_changing_batch_sizes(gd):
+    """One workspace (sized for the largest chunk) serves chunks of any smaller size in any order: a 5-clip chunk, a 2-clip
+    tail, then the same again must reproduce the first pass bit for bit (the SE gate keeps arrival counters in scratch)."""
+    from gesture_b200.engine import _Launcher
+    from gesture_b200.modules import SpeechEncoder
+    from gesture_b200.speech_native import NativeSpeechEncoder
+    th.manual_seed(0)
+    enc = SpeechEncoder(256).eval().cuda()
+    native = NativeSpeechEncoder(enc, _Launcher(), th.device("cuda", 0), chunk=5)
+    wav = th.randn(7, 16000, device="cuda", generator=th.Generator(device="cuda").manual_seed(9))
+    first = native(wav)
+    second = native(wav)
+    third = native(wav[:5])
+    for a, b, c in zip(first, second, third):
+        assert th.isfinite(a).all()
+        assert th.equal(a, b) and th.equal(a[:5], c)
