@@ -9,8 +9,15 @@ One bench "step" = one full 1000-step ancestral chain over the rank's batch of c
 BASELINE.json configs[1]: tedexp-ours, 256 clips, bf16, CUDA-graph replays.  N>1 (torchrun) shards clips: every rank
 samples its own 256 clips (weak scaling) and the generated poses are all-gathered over NCCL inside the timed region.
 `value` times the chain with inputs resident in HBM; `e2e` goes through Generator.generate_sample with pinned HOST
-wav/noise buffers and a device->host read of the poses.  `--impl reference` times the CPU oracle port of the reference's
-sampler (the reference is pure Python and cannot travel to the GPU box) on a bounded sample.
+wav/noise buffers and a device->host read of the poses.
+
+The same JSON line carries a `strong` list: BASELINE configs 3 and 5 - beat-ours, 1 024 clips IN TOTAL split over the N
+ranks, and beat-ours at 4x its window, 512 clips in total - sampled through `distributed.generate_sample_sharded` (host
+buffers in, one NCCL all-gather of the poses, host read), plus a `shard_check`: clips of every rank's shard recomputed
+two at a time on rank 0 must be bit-identical to the gathered result.
+
+`--impl reference` times the UNMODIFIED reference staged under oracle/_ref (oracle/make_ref.py; `kind: "reference"`) on
+the box's host cores - tedexp-ours, 1 clip, as shipped - or, if that copy is absent, the oracle port (`kind: "port"`).
 """
 import argparse
 import json
@@ -52,6 +59,7 @@ def parse():
                     help="denoise steps captured per CUDA graph (0 = the whole chain as one graph, the default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling object (beat-1024 / beat-4x-512 over N ranks)")
     return ap.parse_args()
 
 
@@ -139,26 +147,57 @@ class CpuReference:
                 "cores": th.get_num_threads(), "clips": self.clips, "denoise_steps": denoise_steps}
 
 
+def cpu_model_name():
+    try:
+        for l in open("/proc/cpuinfo"):
+            if l.startswith("model name"):
+                return l.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def reference_sample(workload, clips, denoise_steps):
+    """One bounded sample of the reference's sampler on the host cores: the unmodified reference (oracle/_ref) when it is
+    staged, else the oracle port.  -> (result dict, kind)."""
+    from oracle import ref_runner
+    base = "beat-ours" if workload.startswith("beat") else workload
+    if ref_runner.available() and workload in ref_runner.SHAPES:
+        return ref_runner.time_chain(base, clips, denoise_steps), "reference"
+    ref = CpuReference(workload, clips)
+    ref.sample(1)
+    return ref.sample(denoise_steps), "port"
+
+
 def run_reference(args):
+    """the reference as shipped, 1 clip (BASELINE.json configs[0]), all host threads; every bench step
+    times a bounded run of consecutive denoise steps of the chain (>= 100 in total over the run) and extrapolates x(1000/n)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    clips, per_step = 16, 2
-    ref = CpuReference(args.workload, clips)
-    vals, secs = [], []
+    clips = 1
+    per_step = max(10, -(-100 // max(args.steps, 1)))
+    if args.steps >= 4:
+        per_step = 25
+    vals, secs, kind, cores = [], [], "port", 1
     for it in range(args.warmup + args.steps):
-        r = ref.sample(per_step)
+        r, kind = reference_sample(args.workload, clips, per_step if it >= args.warmup else 3)
+        cores = r["cores"]
         if it >= args.warmup:
             vals.append(r["frames_per_s"])
-            secs.append(r["seconds"])
+            secs.append(r["seconds"] / r["denoise_steps"])
     v = sum(vals) / len(vals)
-    sample = (f"{clips} clips x {per_step} denoise steps per bench step of the {args.workload} chain, as shipped (speech encoder "
-              f"re-run every step), fp32 torch CPU, extrapolated x(1000/{per_step}) to the full chain")
+    what = "the UNMODIFIED reference (oracle/_ref, staged by oracle/make_ref.py)" if kind == "reference" else "the oracle port"
+    sample = (f"{what}: {clips} clip x {per_step} consecutive denoise steps per bench step of the {args.workload} chain "
+              f"({per_step * args.steps} timed steps in total), as shipped (speech encoder re-run every step), fp32 torch CPU, "
+              f"{cores} threads on {cpu_model_name()} ({os.cpu_count()} logical CPUs), extrapolated x(1000/{per_step}) to the full chain")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs) * (1000 / per_step), "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs) * 1000, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload} full 1000-step DDPM chain", "clips_per_sample": clips},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": th.get_num_threads(), "kind": "port", "sample": sample},
+            "ms_per_denoise_step": 1e3 * sum(secs) / len(secs),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                             "cpu_model": cpu_model_name(), "host_cpus": os.cpu_count()},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -205,6 +244,111 @@ def ncu_gemm_traffic(workload):
     except Exception:
         pass
     return None
+
+
+def strong_scaling(args, world, rank, dev, barrier):
+    """BASELINE configs 3 and 5: a FIXED total batch split over the N ranks (`distributed.shard_bounds`), sampled through
+    `distributed.generate_sample_sharded` - full-batch pinned HOST wav / x_T in, every rank runs the whole 1000-step chain
+    on its own slice, one NCCL all-gather of the poses, device->host read of the gathered result.  Also times the chain
+    replay alone (ms per denoise step) and checks that sharding does not change any clip (20-step process, explicit tape:
+    two clips of EVERY rank's shard are recomputed on rank 0 as a 2-clip batch and must be bit-identical)."""
+    import torch.distributed as dist
+    from gesture_b200 import distributed as gdist
+    from gesture_b200.engine import chain_for, release_chains
+    from gesture_b200.generator import Generator
+    from gesture_b200.model_creation import create_model
+    from gesture_b200.synthetic import synthetic_wav
+    out = []
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    for workload, total in (("beat-ours", 1024), ("beat-ours-4x", 512)):
+        params, C, T, L, _ = workload_preset(workload)
+        th.manual_seed(0)
+        model, diffusion, *_ = create_model(C, params)
+        model.eval().to(dev)
+        model.precision = args.precision
+        n_steps = diffusion.num_timesteps
+        gen = Generator(model, diffusion)
+        lo, hi = gdist.shard_bounds(total, world, rank)
+        wav_host = synthetic_wav(total, L, seed=321).pin_memory()
+        x_host = th.randn(total, C, T, generator=th.Generator().manual_seed(77)).pin_memory()
+
+        def one():
+            poses = gdist.generate_sample_sharded(gen, (total, C, T), wav_host, noise=x_host, sample_alg="ddpm", device=dev,
+                                                  progress=False)
+            return poses.cpu()
+        t_cap0 = time.perf_counter()
+        one()  # warm-up: conditioning, graph capture
+        barrier()
+        capture_s = time.perf_counter() - t_cap0
+        one()
+        barrier()
+        n_timed = 2
+        e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_timed):
+            one()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        # chain replay alone on this rank's slice (inputs resident)
+        chain = chain_for(model, diffusion, (hi - lo, C, T), "ddpm", dev)
+        chain.begin(x_host[lo:hi].to(dev), wav_host[lo:hi].to(dev))
+        th.cuda.synchronize()
+        c0, c1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        c0.record()
+        chain.run()
+        c1.record()
+        th.cuda.synchronize()
+        ms_replay = c0.elapsed_time(c1)
+        flops_step = sum(op.flops for op in chain.plan)
+        kernels = len(chain.plan)
+        t = th.tensor([ms, ms_replay], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_replay = t.tolist()
+        release_chains(model)
+        rec = {"workload": f"{workload} full {n_steps}-step DDPM chain, {total} clips in total over {world} GPU(s)", "scaling": "strong",
+               "total_clips": total, "clips_per_gpu": hi - lo, "frames": T,
+               "value": total * T * n_timed / (ms / 1e3), "unit": UNIT, "ms_per_chain": ms / n_timed,
+               "ms_per_denoise_step": ms_replay / n_steps, "chain_replay_ms": ms_replay, "kernels_per_denoise_step": kernels,
+               "first_call_s": capture_s,
+               "path": "distributed.generate_sample_sharded (pinned host wav/x_T -> shard -> chain -> all_gather -> host)",
+               "h2d_bytes_per_chain": (wav_host[lo:hi].numel() + x_host[lo:hi].numel()) * 4, "d2h_bytes_per_chain": total * T * C * 4,
+               "step_flops_per_gpu": flops_step,
+               "roofline_frac_step": flops_step / (ms_replay / n_steps * 1e-3) / 1e12 / peak_tf}
+        # sharding must not change a clip: short process with an explicit tape, every shard spot-checked on rank 0
+        if workload == "beat-ours":
+            from gesture_b200.presets import preset
+            p20, _, _, _ = preset("beat-ours")
+            p20["Diffusion"]["timestep_respacing"] = "ddim20"
+            th.manual_seed(0)
+            m20, d20, *_ = create_model(C, p20)
+            m20.eval().to(dev)
+            g20 = Generator(m20, d20)
+            gt = th.Generator().manual_seed(78)
+            tape = th.randn(20, total, C, T, generator=gt)
+            full = gdist.generate_sample_sharded(g20, (total, C, T), wav_host, noise=x_host, noise_tape=tape, sample_alg="ddpm",
+                                                 device=dev, progress=False)
+            ok, checked = True, 0
+            if rank == 0:
+                for r in range(world):
+                    rlo, rhi = gdist.shard_bounds(total, world, r)
+                    two = g20.generate_sample((2, C, T), wav_host[rlo:rlo + 2], noise=x_host[rlo:rlo + 2], noise_tape=tape[:, rlo:rlo + 2],
+                                              sample_alg="ddpm", device=dev, progress=False)
+                    ok = ok and bool(th.equal(two, full[rlo:rlo + 2]))
+                    checked += 1
+            barrier()
+            release_chains(m20)
+            rec["shard_check"] = {"process": "beat-ours, 20-step respaced ancestral chain, explicit noise tape", "shards_checked": checked,
+                                  "bit_identical_to_2_clip_recompute": ok}
+        out.append(rec)
+    return out
+
 
 
 def run_b200(args):
@@ -311,13 +455,24 @@ def run_b200(args):
         e2e = {"value": world * clips * T * n_e2e / (ems / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": wav_host.numel() * 4 + x_host.numel() * 4, "d2h_bytes_per_step": clips * T * C * 4}
 
+    agg_pre = kernel_breakdown(chain) if rank == 0 else None
+    plan_len, _flops_pre, speech_impl = len(chain.plan), sum(op.flops for op in chain.plan), chain.speech_impl
+    graph_info = dict(chain.graph_info)
+    strong = None
+    if not args.no_strong:
+        # free the headline chain's tape / graph first (the beat-1024 tape is 20 GB, beat-4x-512 40 GB)
+        from gesture_b200.engine import release_chains
+        del chain
+        release_chains(model)
+        strong = strong_scaling(args, world, rank, dev, barrier)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     # roofline of the dominant kernel class (the tcgen05 GEMM), measured live with CUDA events
-    agg = kernel_breakdown(chain)
+    agg = agg_pre
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -342,13 +497,14 @@ def run_b200(args):
 
     cpu = None
     if not args.no_cpu_baseline:
-        ref = CpuReference(args.workload, 1)
-        ref.sample(2)  # warm-up
-        r = ref.sample(40 if args.workload == "tedexp-ours" else 150)
-        cpu = {"value": r["frames_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-               "sample": f"1 clip, first {r['denoise_steps']} of 1000 denoise steps as shipped (speech encoder re-run every step), "
-                         f"{r['seconds']:.1f} s CPU, extrapolated to the full chain; {r['ms_per_denoise_step']:.1f} ms/denoise-step",
-               "host_cpus": os.cpu_count()}
+        th.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; the CPU leg uses every host core
+        r, kind = reference_sample(args.workload, 1, 100 if args.workload == "tedexp-ours" else 150)
+        cpu = {"value": r["frames_per_s"], "unit": UNIT, "cores": r["cores"], "kind": kind,
+               "sample": f"{'the unmodified reference (oracle/_ref)' if kind == 'reference' else 'the oracle port'}: 1 clip, "
+                         f"{r['denoise_steps']} consecutive denoise steps of the 1000-step chain as shipped (speech encoder re-run "
+                         f"every step), {r['seconds']:.1f} s CPU, extrapolated to the full chain; "
+                         f"{r['ms_per_denoise_step']:.1f} ms/denoise-step",
+               "cpu_model": cpu_model_name(), "host_cpus": os.cpu_count()}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_chain, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -360,13 +516,18 @@ def run_b200(args):
                        "parallelism": f"clip-sharded x{world}, all_gather of poses"},
             "ms_per_denoise_step": ms_replay / n_steps, "chain_replay_ms": ms_replay,
             # per chain, outside the 1000 replays: speech encoder + conditioning GEMMs + on-device noise tape
-            "chain_begin_ms": ms_per_chain - ms_replay, "speech_encoder": chain.speech_impl,
+            "chain_begin_ms": ms_per_chain - ms_replay, "speech_encoder": speech_impl,
+            "graph": graph_info,
             "step_flops_executed": total_flops,
             "model_tflops_chain": total_flops * n_steps / (ms_replay * 1e-3) / 1e12,
             "clocks": clk.summary(), "e2e": e2e,
-            "gpu_launches": len(chain.plan) * n_steps * args.steps, "kernels_per_denoise_step": len(chain.plan),
+            "gpu_launches": plan_len * n_steps * args.steps, "kernels_per_denoise_step": plan_len,
             "lib_launch_counter": int(lib.gd_launch_count()),
-            "roofline": roofline, "kernel_breakdown": breakdown, "cpu_baseline": cpu}
+            "roofline": roofline, "kernel_breakdown": breakdown,
+            "kernel_breakdown_note": "eager step, one CUDA event between consecutive launches: a LOWER bound on the in-graph rates "
+                                     "(the graph runs the step faster: no event gaps, concurrent branches overlap); in-graph per-class "
+                                     "times from CUPTI are in profiles/r02_ingraph_breakdown_*.json",
+            "strong": strong, "cpu_baseline": cpu}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GD_ABI_VERSION 3
+#define GD_ABI_VERSION 4
 
 enum gd_status {
     GD_OK = 0,
@@ -115,6 +115,8 @@ typedef struct gd_ddpm_desc {
     const float* xa_add;      /* optional (N, C, T) fp32 added to x' before the bf16 cast into xa_bf16: the
                                  loop-invariant `proj([inpaint_pose*mask | mask])` that Speech2GestureModelInpaint
                                  adds to its input (models/model.py:155-166)                                        */
+    float* mean_out;          /* ABI 4, optional (N, C, T): posterior mean (`mean` of p_mean_variance, :276-285)      */
+    float* raw_x0_out;        /* ABI 4, optional (N, C, T): x0 BEFORE the in-paint blend (`raw_x_start`, :254)        */
 } gd_ddpm_desc;
 
 /* Standalone update from an eps tensor laid out (N, C, T). */
@@ -164,7 +166,7 @@ int gd_linear_resid_ln(const gd_linear_desc* d, const gd_ln_desc* ln, void* stre
  * O = S·V.  The token sequence of a clip is the concatenation of up to two row segments
  * (tedexp joint attention over [x ; memory], models/nn.py:105-113); the conv runs across the seam.
  *   q/k/v[s]   bf16, row (clip*rows[s] + i) at ptr + row*ld, head h at columns [h*d_k, (h+1)*d_k)
- *   out[s]     bf16, same row structure as q
+ *   out[s]     bf16, same row structure as q (row clip*q_rows[s] + i); out[1] may be NULL (halo segment, see below)
  *   conv_*     fp32 [d_k, 3] taps and [d_k] bias per projection
  * d_k in {32, 64}; total keys per clip <= 160.
  * ------------------------------------------------------------------------------------------ */
@@ -186,6 +188,13 @@ typedef struct gd_attn_desc {
     const float* conv_bv;
     int32_t n_clips, heads, d_k;
     float scale;
+    /* ABI 4.  q_clip_stride[s] > 0: consecutive clips of query segment s are that many rows apart (default q_rows[s]).
+     * A query segment with out[s] == NULL is a conv HALO: its rows take part in the depth-wise conv of the
+     * concatenated query sequence but get no attention output.  The last tedexp layer needs it: only the pose rows are
+     * read after the joint attention (models/nn.py:445-447), but the conv3 of the last pose frame reaches memory row 0
+     * (models/nn.py:105-113, transformer.py:19-44), so q[1] = memory row 0 of every clip, q_rows[1] = 1,
+     * q_clip_stride[1] = memory rows per clip, out[1] = NULL. */
+    int32_t q_clip_stride[2];
 } gd_attn_desc;
 
 int gd_dconv_attention(const gd_attn_desc* d, void* stream);

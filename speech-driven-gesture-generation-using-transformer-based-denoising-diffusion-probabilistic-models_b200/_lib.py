@@ -25,7 +25,7 @@ class DdpmDesc(C.Structure):
                 ("coef_C2", c_vp), ("sigma", c_vp), ("step_ptr", c_vp), ("n_clips", c_i32), ("C", c_i32),
                 ("T", c_i32), ("eps_out", c_vp), ("x0_out", c_vp), ("xa_bf16", c_vp), ("ld_xa", c_i32),
                 ("inpaint_seed", c_vp), ("inpaint_mask", c_vp), ("inpaint_factor", c_vp), ("clip_x0", c_f32),
-                ("xa_add", c_vp)]
+                ("xa_add", c_vp), ("mean_out", c_vp), ("raw_x0_out", c_vp)]
 
 
 class LnDesc(C.Structure):
@@ -37,7 +37,8 @@ class AttnDesc(C.Structure):
     _fields_ = [("q", c_vp * 2), ("q_rows", c_i32 * 2), ("q_ld", c_i32 * 2), ("k", c_vp * 2), ("v", c_vp * 2),
                 ("kv_rows", c_i32 * 2), ("kv_ld", c_i32 * 2), ("out", c_vp * 2), ("out_ld", c_i32 * 2),
                 ("conv_wq", c_vp), ("conv_bq", c_vp), ("conv_wk", c_vp), ("conv_bk", c_vp), ("conv_wv", c_vp),
-                ("conv_bv", c_vp), ("n_clips", c_i32), ("heads", c_i32), ("d_k", c_i32), ("scale", c_f32)]
+                ("conv_bv", c_vp), ("n_clips", c_i32), ("heads", c_i32), ("d_k", c_i32), ("scale", c_f32),
+                ("q_clip_stride", c_i32 * 2)]
 
 
 class ConvDesc(C.Structure):
@@ -50,6 +51,7 @@ class ConvDesc(C.Structure):
 
 
 ACT_NONE, ACT_RELU2, ACT_SILU = 0, 1, 2
+ABI_VERSION = 4  # include/gd_b200.h GD_ABI_VERSION
 
 # name -> (restype, argtypes); every symbol include/gd_b200.h declares
 SYMBOLS = {
@@ -100,7 +102,7 @@ def load():
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype, fn.argtypes = res, args
-    if lib.gd_abi_version() != 3:
+    if lib.gd_abi_version() != ABI_VERSION:
         raise GdError("libgd_b200.so ABI version mismatch")
     _lib = lib
     return lib

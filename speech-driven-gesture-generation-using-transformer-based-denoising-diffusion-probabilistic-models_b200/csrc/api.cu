@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 namespace gd {
 
@@ -53,9 +54,24 @@ int check_device() {
     return GD_OK;
 }
 
+static thread_local const char* g_kind = "";
+KindScope::KindScope(const char* kind) : prev(g_kind) { g_kind = kind; }
+KindScope::~KindScope() { g_kind = prev; }
+
 static bool pdl_enabled() {
     const char* e = getenv("GD_PDL");
-    return !(e && e[0] == '0');
+    if (e && e[0] == '0') return false;
+    const char* off = getenv("GD_PDL_OFF");  // comma-separated kernel families launched without early start
+    if (off && g_kind[0]) {
+        const size_t n = strlen(g_kind);
+        for (const char* q = off; *q;) {
+            const char* c = strchr(q, ',');
+            const size_t len = c ? (size_t)(c - q) : strlen(q);
+            if (len == n && strncmp(q, g_kind, n) == 0) return false;
+            q += len + (c ? 1 : 0);
+        }
+    }
+    return true;
 }
 
 void fill_launch(LaunchCfg& L, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x) {

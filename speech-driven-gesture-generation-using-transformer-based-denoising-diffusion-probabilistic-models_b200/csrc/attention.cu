@@ -18,13 +18,13 @@ constexpr int ATT_MAX_WARPS = 5;  // 4 or 5 warps per CTA (chosen per launch), s
 
 
 // Raw (pre-conv) storage of 8 consecutive elements of a projected row: one 16-B load for bf16, two for fp32.
-// Loads go through the non-coherent path (ld.global.nc) so the compiler may batch them ahead of the smem stores.
+// Loads are L2-coherent (ld.global.cg): Q/K/V rows are written by the previous kernel of the chain (common.cuh, PDL and L1).
 template <typename T>
 struct Raw8;
 template <>
 struct Raw8<__nv_bfloat16> {
     uint4 u;
-    __device__ __forceinline__ void load(const __nv_bfloat16* p) { u = __ldg(reinterpret_cast<const uint4*>(p)); }
+    __device__ __forceinline__ void load(const __nv_bfloat16* p) { u = __ldcg(reinterpret_cast<const uint4*>(p)); }
     __device__ __forceinline__ void zero() { u = make_uint4(0, 0, 0, 0); }
     __device__ __forceinline__ void unpack(float (&f)[8]) const {
         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -39,8 +39,8 @@ template <>
 struct Raw8<float> {
     float4 a, b;
     __device__ __forceinline__ void load(const float* p) {
-        a = __ldg(reinterpret_cast<const float4*>(p));
-        b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        a = __ldcg(reinterpret_cast<const float4*>(p));
+        b = __ldcg(reinterpret_cast<const float4*>(p) + 1);
     }
     __device__ __forceinline__ void zero() { a = b = make_float4(0.f, 0.f, 0.f, 0.f); }
     __device__ __forceinline__ void unpack(float (&f)[8]) const {
@@ -66,15 +66,15 @@ __device__ __forceinline__ void raw_row8(Raw8<T>& r, const T* base0, const T* ba
 // 16-B loads in flight per thread), then the 3-tap FIR slides over them in registers (3 FFMA per element).
 template <typename T, int DK>
 __device__ __forceinline__ void conv_stage(__nv_bfloat16* dst, int L, int L_pad, const void* const (&seg)[2],
-                                           const int (&rows)[2], const int (&ld)[2], int clip, int head,
+                                           const int (&rows)[2], const int (&stride)[2], const int (&ld)[2], int clip, int head,
                                            const float* s_taps /* [DK*3] */, const float* s_bias /* [DK] */) {
     constexpr int STR = DK + 8;
     constexpr int CH = DK / 8;
     constexpr int SEGT = sizeof(T) == 2 ? 8 : 4;
     const int n_seg = (L_pad + SEGT - 1) / SEGT;
     const int rows0 = rows[0], ld0 = ld[0], ld1 = ld[1];
-    const T* clip0 = reinterpret_cast<const T*>(seg[0]) + (size_t)clip * rows0 * ld0 + head * DK;
-    const T* clip1 = seg[1] ? reinterpret_cast<const T*>(seg[1]) + (size_t)clip * rows[1] * ld1 + head * DK : clip0;
+    const T* clip0 = reinterpret_cast<const T*>(seg[0]) + (size_t)clip * stride[0] * ld0 + head * DK;
+    const T* clip1 = seg[1] ? reinterpret_cast<const T*>(seg[1]) + (size_t)clip * stride[1] * ld1 + head * DK : clip0;
     for (int item = threadIdx.x; item < n_seg * CH; item += blockDim.x) {
         const int ch = item % CH, sg = item / CH;
         const int c0 = ch * 8, p0 = sg * SEGT;
@@ -163,9 +163,9 @@ __global__ void __launch_bounds__(ATT_MAX_WARPS * 32, 3) dconv_attention_kernel(
     pdl_launch_dependents();
     pdl_wait();  // the conv taps are weights; everything below reads the previous kernel's output
     __syncthreads();
-    conv_stage<T, DK>(sq, p.Lq, Lq_pad, p.q, p.q_rows, p.q_ld, clip, head, s_taps, s_taps + DK * 3);
-    conv_stage<T, DK>(sk, p.Lk, LK_PAD, p.k, p.kv_rows, p.kv_ld, clip, head, s_taps + DK * 4, s_taps + DK * 7);
-    conv_stage<T, DK>(sv, p.Lk, LK_PAD, p.v, p.kv_rows, p.kv_ld, clip, head, s_taps + DK * 8, s_taps + DK * 11);
+    conv_stage<T, DK>(sq, p.Lq, Lq_pad, p.q, p.q_rows, p.q_stride, p.q_ld, clip, head, s_taps, s_taps + DK * 3);
+    conv_stage<T, DK>(sk, p.Lk, LK_PAD, p.k, p.kv_rows, p.kv_rows, p.kv_ld, clip, head, s_taps + DK * 4, s_taps + DK * 7);
+    conv_stage<T, DK>(sv, p.Lk, LK_PAD, p.v, p.kv_rows, p.kv_rows, p.kv_ld, clip, head, s_taps + DK * 8, s_taps + DK * 11);
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(ATT_MAX_WARPS * 32, 3) dconv_attention_kernel(
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             const int i = qt * 16 + g + half * 8;
-            if (i < p.Lq) {
+            if (i < p.Lq && (i < p.q_rows[0] || p.out[1])) {  // a segment without an output is a conv halo only
                 __nv_bfloat16* orow = (i < p.q_rows[0])
                                           ? p.out[0] + ((size_t)clip * p.q_rows[0] + i) * p.out_ld[0]
                                           : p.out[1] + ((size_t)clip * p.q_rows[1] + (i - p.q_rows[0])) * p.out_ld[1];
@@ -426,8 +426,8 @@ dconv_attention_tma_kernel(const __grid_constant__ CUtensorMap tm_q0, const __gr
         uint8_t* raw_v = raw_q + geo.raw_v_off;
         uint64_t* bar = &full_bar[stage];
         mbar_arrive_expect_tx(bar, geo.tx_bytes);
-        tma_load_2d(raw_q + ATT2_ROW_BYTES, &tm_q0, bar, col0, clip * p.q_rows[0]);
-        if (p.q_rows[1]) tma_load_2d(raw_q + (1 + p.q_rows[0]) * ATT2_ROW_BYTES, &tm_q1, bar, col0, clip * p.q_rows[1]);
+        tma_load_2d(raw_q + ATT2_ROW_BYTES, &tm_q0, bar, col0, clip * p.q_stride[0]);
+        if (p.q_rows[1]) tma_load_2d(raw_q + (1 + p.q_rows[0]) * ATT2_ROW_BYTES, &tm_q1, bar, col0, clip * p.q_stride[1]);
         tma_load_2d(raw_k + ATT2_ROW_BYTES, &tm_k0, bar, col0, clip * p.kv_rows[0]);
         tma_load_2d(raw_v + ATT2_ROW_BYTES, &tm_v0, bar, col0, clip * p.kv_rows[0]);
         if (p.kv_rows[1]) {
@@ -552,7 +552,7 @@ dconv_attention_tma_kernel(const __grid_constant__ CUtensorMap tm_q0, const __gr
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int i = qt * 16 + g + half * 8;
-                if (i < Lq) {
+                if (i < Lq && (i < p.q_rows[0] || p.out[1])) {  // a segment without an output is a conv halo only
                     __nv_bfloat16* orow = (i < p.q_rows[0])
                                               ? p.out[0] + ((size_t)clip * p.q_rows[0] + i) * p.out_ld[0]
                                               : p.out[1] + ((size_t)clip * p.q_rows[1] + (i - p.q_rows[0])) * p.out_ld[1];
@@ -617,8 +617,9 @@ static int launch_attention_tma(const AttnParams& p, int n_clips, cudaStream_t s
     CUtensorMap tq[2], tk[2], tv[2];
     for (int sgi = 0; sgi < 2; ++sgi) {
         const int has_q = p.q_rows[sgi] > 0, has_k = p.kv_rows[sgi] > 0;
-        int rc = make_rows_tmap(&tq[sgi], has_q ? p.q[sgi] : p.q[0], (uint64_t)n_clips * p.q_rows[has_q ? sgi : 0],
-                                (uint64_t)p.heads * DK, p.q_ld[has_q ? sgi : 0], p.q_rows[has_q ? sgi : 0]);
+        const int qs = has_q ? sgi : 0;
+        int rc = make_rows_tmap(&tq[sgi], p.q[qs], (uint64_t)(n_clips - 1) * p.q_stride[qs] + p.q_rows[qs],
+                                (uint64_t)p.heads * DK, p.q_ld[qs], p.q_rows[qs]);
         if (rc) return rc;
         rc = make_rows_tmap(&tk[sgi], has_k ? p.k[sgi] : p.k[0], (uint64_t)n_clips * p.kv_rows[has_k ? sgi : 0],
                             (uint64_t)p.heads * DK, p.kv_ld[has_k ? sgi : 0], p.kv_rows[has_k ? sgi : 0]);
@@ -684,7 +685,8 @@ static int run_attention(const gd_attn_desc* d, bool fp32_in, void* stream) {
     if (!d->conv_wq || !d->conv_bq || !d->conv_wk || !d->conv_bk || !d->conv_wv || !d->conv_bv)
         return set_error(GD_ERR_INVALID, "gd_dconv_attention: conv taps missing");
     if (d->n_clips <= 0 || d->heads <= 0) return set_error(GD_ERR_INVALID, "gd_dconv_attention: bad clip/head count");
-    if ((d->q[1] && !d->out[1]) || (d->k[1] && !d->v[1])) return set_error(GD_ERR_INVALID, "gd_dconv_attention: segment 1 incomplete");
+    if (d->k[1] && !d->v[1]) return set_error(GD_ERR_INVALID, "gd_dconv_attention: segment 1 incomplete");
+    KindScope kind_scope("attn");
     AttnParams p{};
     const int align = fp32_in ? 4 : 8;  // 16-byte row loads
     for (int s = 0; s < 2; ++s) {
@@ -693,6 +695,8 @@ static int run_attention(const gd_attn_desc* d, bool fp32_in, void* stream) {
         p.q_rows[s] = d->q[s] ? d->q_rows[s] : 0;
         p.kv_rows[s] = d->k[s] ? d->kv_rows[s] : 0;
         p.q_ld[s] = d->q_ld[s], p.kv_ld[s] = d->kv_ld[s], p.out_ld[s] = d->out_ld[s];
+        p.q_stride[s] = d->q_clip_stride[s] > 0 ? d->q_clip_stride[s] : p.q_rows[s];
+        if (p.q_stride[s] < p.q_rows[s]) return set_error(GD_ERR_INVALID, "gd_dconv_attention: q_clip_stride < q_rows");
         if ((d->q[s] && (d->q_ld[s] % align || (reinterpret_cast<uintptr_t>(d->q[s]) & 15) || d->out_ld[s] % 2)) ||
             (d->k[s] && (d->kv_ld[s] % align || ((reinterpret_cast<uintptr_t>(d->k[s]) | reinterpret_cast<uintptr_t>(d->v[s])) & 15))))
             return set_error(GD_ERR_INVALID, "gd_dconv_attention: q/k/v rows must be 16-byte aligned");
@@ -707,7 +711,8 @@ static int run_attention(const gd_attn_desc* d, bool fp32_in, void* stream) {
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     // bf16 rows whose segments fit a TMA box go to the persistent TMA-fed kernel
     const int variant = attention_variant();
-    if (!fp32_in && variant == 3 && d->d_k == 64 && p.q_rows[0] <= 256 && p.q_rows[1] <= 256 && p.kv_rows[0] <= 256 &&
+    const bool halo = (p.q_rows[1] > 0 && !p.out[1]) || p.q_stride[0] != p.q_rows[0] || p.q_stride[1] != p.q_rows[1];
+    if (!fp32_in && variant == 3 && !halo && d->d_k == 64 && p.q_rows[0] <= 256 && p.q_rows[1] <= 256 && p.kv_rows[0] <= 256 &&
         p.kv_rows[1] <= 256 && p.Lq <= 144 && attention_tc_smem_bytes(p) <= 232448)
         return launch_attention_tc(p, d->n_clips, s);
     const bool tma_ok = !fp32_in && variant >= 2 && p.q_rows[0] <= 256 && p.q_rows[1] <= 256 &&

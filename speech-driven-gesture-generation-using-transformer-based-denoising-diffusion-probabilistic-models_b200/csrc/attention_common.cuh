@@ -13,6 +13,7 @@ struct AttnParams {
     const void* v[2];
     __nv_bfloat16* out[2];
     int q_rows[2], q_ld[2], kv_rows[2], kv_ld[2], out_ld[2];
+    int q_stride[2];  // rows between consecutive clips of a query segment (== q_rows unless the segment is a halo view)
     const float *wq, *bq, *wk, *bk, *wv, *bv;
     int heads, Lq, Lk;
     float scale_log2;  // d_k^-1/2 * log2(e)

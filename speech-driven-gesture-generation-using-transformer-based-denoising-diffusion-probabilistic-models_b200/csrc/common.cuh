@@ -19,7 +19,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 // set-up: barrier init, TMEM allocation, tensor-map prefetch, weight-only preloads) while the previous kernel of the
 // stream is still draining.  pdl_wait() blocks until that kernel has completed and its writes are visible; it MUST
 // precede the first access to any buffer another kernel of the chain reads or writes.
+//
+// L1 and early launch (found in round 2, profiles/r02_determinism_bisect.jsonl): a CTA of kernel k+2 can become resident
+// on an SM while kernel k is still running there.  Lines that kernel k then pulls into that SM's L1 with ordinary
+// (ld.global.ca / .nc) loads survive until k+2 passes its pdl_wait(), so k+2 could read a value that kernel k+1 has since
+// overwritten - the per-step scatter read the step counter that the DDPM epilogue two kernels earlier had cached, and
+// scattered the PREVIOUS step's timestep row.  Every load of a buffer that another kernel of the chain writes therefore
+// goes through L2 (ld.global.cg: __ldcg / load_step / TMA); __ldg and plain loads are for weights and tables only.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ int load_step(const int* step_ptr) { return __ldcg(step_ptr); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 
 // ---------------------------------------------------------------- clusters

@@ -26,8 +26,10 @@ __device__ __forceinline__ DdpmStepCoefs ddpm_load_coefs(const gd_ddpm_desc& u, 
 // One element of the update. `seed`, `m`, `f` describe the optional in-paint blend
 // (generator.py:271-280): x0 <- (1-f)*m*seed + f*m*x0 + (1-m)*x0, evaluated left to right.
 __device__ __forceinline__ float ddpm_update_elem(const DdpmStepCoefs& c, float x, float eps, float z, bool inpaint,
-                                                  float seed, float m, float f, float clip, float* x0_out) {
+                                                  float seed, float m, float f, float clip, float* x0_out,
+                                                  float* mean_out = nullptr, float* raw_x0_out = nullptr) {
     float x0 = __fsub_rn(__fmul_rn(c.A, x), __fmul_rn(c.B, eps));
+    if (raw_x0_out) *raw_x0_out = x0;
     if (inpaint) {
         float a = __fmul_rn(__fmul_rn(__fsub_rn(1.0f, f), m), seed);
         float b = __fmul_rn(__fmul_rn(f, m), x0);
@@ -37,6 +39,7 @@ __device__ __forceinline__ float ddpm_update_elem(const DdpmStepCoefs& c, float 
     if (clip > 0.0f) x0 = fminf(fmaxf(x0, -clip), clip);
     if (x0_out) *x0_out = x0;
     float mean = __fadd_rn(__fmul_rn(c.C1, x0), __fmul_rn(c.C2, x));
+    if (mean_out) *mean_out = mean;
     return __fadd_rn(mean, __fmul_rn(c.sig, z));
 }
 

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
         const int row = min(row0 + r, M - 1);
         const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ldx);
 #pragma unroll
-        for (int i = 0; i < V; ++i) v[r][i] = xr[i * 32 + lane];
+        for (int i = 0; i < V; ++i) v[r][i] = __ldcg(xr + i * 32 + lane);  // L2-coherent: see common.cuh (PDL and L1)
     }
     const float4* g4 = reinterpret_cast<const float4*>(gamma);
     const float4* b4 = reinterpret_cast<const float4*>(beta);
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) ddpm_update_kernel(const gd_ddpm_desc u, 
                                                           int c_span) {
     pdl_launch_dependents();
     pdl_wait();
-    const int t = *u.step_ptr;
+    const int t = load_step(u.step_ptr);
     const DdpmStepCoefs cf = ddpm_load_coefs(u, t);
     const size_t total = (size_t)u.n_clips * c_span * u.T;
     const size_t tape_base = (size_t)t * u.n_clips * u.C * u.T;
@@ -88,12 +88,14 @@ __global__ void __launch_bounds__(256) ddpm_update_kernel(const gd_ddpm_desc u, 
                 seed = __ldg(u.inpaint_seed + ((size_t)clip * u.T + frame) * u.C + c);
             }
             const float z = u.noise_tape ? __ldg(u.noise_tape + tape_base + idx) : 0.f;
-            const float e = eps[idx];
-            float x0;
-            xnext = ddpm_update_elem(cf, u.x[idx], e, z, inpaint, seed, m, f, u.clip_x0, &x0);
+            const float e = __ldcg(eps + idx);
+            float x0, mean, raw;
+            xnext = ddpm_update_elem(cf, __ldcg(u.x + idx), e, z, inpaint, seed, m, f, u.clip_x0, &x0, &mean, &raw);
             u.x[idx] = xnext;
             if (u.eps_out) u.eps_out[idx] = e;
             if (u.x0_out) u.x0_out[idx] = x0;
+            if (u.mean_out) u.mean_out[idx] = mean;
+            if (u.raw_x0_out) u.raw_x0_out[idx] = raw;
         }
         if (u.xa_bf16)
             reinterpret_cast<__nv_bfloat16*>(u.xa_bf16)[((size_t)clip * u.T + frame) * u.ld_xa + c] =
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(256) scatter_row_f32_kernel(float* __restrict_
                                                               int rows_per_clip, int row_index, int width, int ld) {
     pdl_launch_dependents();
     pdl_wait();
-    const int t = *step_ptr;
+    const int t = load_step(step_ptr);
     const int w4 = width >> 2;
     const float4* trow = reinterpret_cast<const float4*>(table + (size_t)t * width);
     if (init) {
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(256) scatter_row_f32_kernel(float* __restrict_
             const int j = (int)(i % w4);
             const size_t row = i / w4;
             const bool is_t = (int)(row % rows_per_clip) == row_index;
-            const float4 val = is_t ? __ldg(trow + j) : reinterpret_cast<const float4*>(init + row * ld)[j];
+            const float4 val = is_t ? __ldg(trow + j) : __ldcg(reinterpret_cast<const float4*>(init + row * ld) + j);
             reinterpret_cast<float4*>(dst + row * ld)[j] = val;
         }
     } else {
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(256) scatter_row_bf16_kernel(__nv_bfloat16* __
                                                                int rows_per_clip, int row_index, int width, int ld) {
     pdl_launch_dependents();
     pdl_wait();
-    const int t = *step_ptr;
+    const int t = load_step(step_ptr);
     const int w8 = width >> 3;
     const uint4* trow = reinterpret_cast<const uint4*>(table + (size_t)t * width);
     const size_t total = (size_t)n_clips * w8;
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(256) pack_pose_rows_kernel(const float* __rest
         float v = 0.f;
         if (c < C) {
             const size_t idx = (clip * C + c) * T + frame;
-            v = add ? x[idx] + __ldg(add + idx) : x[idx];
+            v = add ? __ldcg(x + idx) + __ldg(add + idx) : __ldcg(x + idx);
         }
         xa[i] = __float2bfloat16_rn(v);
     }
@@ -177,14 +179,14 @@ __global__ void __launch_bounds__(256) cast_rows_bf16_kernel(const float* __rest
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % cols_padded);
         const size_t r = i / cols_padded;
-        dst[r * ldd + c] = __float2bfloat16_rn(c < cols ? src[r * lds + c] : 0.f);
+        dst[r * ldd + c] = __float2bfloat16_rn(c < cols ? __ldcg(src + r * lds + c) : 0.f);
     }
 }
 
 __global__ void step_add_kernel(int* step_ptr, int delta) {
     pdl_launch_dependents();
     pdl_wait();
-    *step_ptr += delta;
+    *step_ptr = load_step(step_ptr) + delta;
 }
 
 static inline int grid_for(size_t total, int block) {
@@ -199,6 +201,7 @@ using namespace gd;
 
 extern "C" int gd_layernorm(const float* x, int32_t ldx, const float* gamma, const float* beta, void* out_bf16,
                             int32_t ldo, int32_t M, int32_t D, float eps, void* stream) {
+    gd::KindScope kind_scope("ln");
     if (!x || !gamma || !beta || !out_bf16) return set_error(GD_ERR_INVALID, "gd_layernorm: null pointer");
     if (M <= 0) return set_error(GD_ERR_INVALID, "gd_layernorm: M <= 0");
     if (ldx % 4 || ldo % 4 || ldx < D || ldo < D) return set_error(GD_ERR_INVALID, "gd_layernorm: bad row stride");
@@ -223,6 +226,7 @@ extern "C" int gd_layernorm(const float* x, int32_t ldx, const float* gamma, con
 }
 
 extern "C" int gd_ddpm_update(const gd_ddpm_desc* u, const float* eps, void* stream) {
+    gd::KindScope kind_scope("ddpm");
     int rc = validate_ddpm(u);
     if (rc) return rc;
     if (!eps) return set_error(GD_ERR_INVALID, "gd_ddpm_update: eps is null");
@@ -241,6 +245,7 @@ extern "C" int gd_ddpm_update(const gd_ddpm_desc* u, const float* eps, void* str
 extern "C" int gd_scatter_step_row_f32(float* dst, const float* init, const float* table, const int32_t* step_ptr,
                                        int32_t n_clips, int32_t rows_per_clip, int32_t row_index, int32_t width,
                                        int32_t ld, void* stream) {
+    gd::KindScope kind_scope("scatter");
     if (!dst || !table || !step_ptr) return set_error(GD_ERR_INVALID, "gd_scatter_step_row_f32: null pointer");
     if (width % 4 || ld % 4 || ld < width || row_index < 0 || row_index >= rows_per_clip || n_clips <= 0)
         return set_error(GD_ERR_INVALID, "gd_scatter_step_row_f32: bad shape");
@@ -255,6 +260,7 @@ extern "C" int gd_scatter_step_row_f32(float* dst, const float* init, const floa
 extern "C" int gd_scatter_step_row_bf16(void* dst, const void* table, const int32_t* step_ptr, int32_t n_clips,
                                         int32_t rows_per_clip, int32_t row_index, int32_t width, int32_t ld,
                                         void* stream) {
+    gd::KindScope kind_scope("scatter");
     if (!dst || !table || !step_ptr) return set_error(GD_ERR_INVALID, "gd_scatter_step_row_bf16: null pointer");
     if (width % 8 || ld % 8 || ld < width || row_index < 0 || row_index >= rows_per_clip || n_clips <= 0)
         return set_error(GD_ERR_INVALID, "gd_scatter_step_row_bf16: bad shape");
@@ -269,6 +275,7 @@ extern "C" int gd_scatter_step_row_bf16(void* dst, const void* table, const int3
 
 extern "C" int gd_pack_pose_rows_add(const float* x, const float* add, void* xa_bf16, int32_t n_clips, int32_t C, int32_t T,
                                      int32_t ld, void* stream) {
+    gd::KindScope kind_scope("pack");
     if (!x || !xa_bf16 || n_clips <= 0 || C <= 0 || T <= 0 || ld < C)
         return set_error(GD_ERR_INVALID, "gd_pack_pose_rows: bad argument");
     const size_t total = (size_t)n_clips * T * ld;
@@ -286,6 +293,7 @@ extern "C" int gd_pack_pose_rows(const float* x, void* xa_bf16, int32_t n_clips,
 
 extern "C" int gd_cast_rows_bf16(const float* src, int32_t lds, void* dst, int32_t ldd, int32_t rows, int32_t cols,
                                  int32_t cols_padded, void* stream) {
+    gd::KindScope kind_scope("pack");
     if (!src || !dst || rows <= 0 || cols <= 0 || cols_padded < cols || ldd < cols_padded || lds < cols)
         return set_error(GD_ERR_INVALID, "gd_cast_rows_bf16: bad argument");
     const size_t total = (size_t)rows * cols_padded;
@@ -297,6 +305,7 @@ extern "C" int gd_cast_rows_bf16(const float* src, int32_t lds, void* dst, int32
 }
 
 extern "C" int gd_step_add(int32_t* step_ptr, int32_t delta, void* stream) {
+    gd::KindScope kind_scope("step");
     if (!step_ptr) return set_error(GD_ERR_INVALID, "gd_step_add: null pointer");
     GD_CUDA_CHECK(launch_k(step_add_kernel, 1, 1, 0, reinterpret_cast<cudaStream_t>(stream), 1, step_ptr, delta));
     count_launch();

@@ -419,6 +419,7 @@ static int launch_resid_ln(const gd_linear_desc* d, const gd_ln_desc* ln, cudaSt
 using namespace gd;
 
 extern "C" int gd_linear_resid_ln(const gd_linear_desc* d, const gd_ln_desc* ln, void* stream) {
+    gd::KindScope kind_scope("gemm");
     if (!d || !ln || !d->A || !d->W) return set_error(GD_ERR_INVALID, "gd_linear_resid_ln: null descriptor/operand");
     if (d->M <= 0 || d->K <= 0 || d->K % RL_BLOCK_K) return set_error(GD_ERR_INVALID, "gd_linear_resid_ln: K must be a positive multiple of 64");
     if (d->N != 256 && d->N != 512) return set_error(GD_ERR_INVALID, "gd_linear_resid_ln: N=%d must be the model width 256 or 512", d->N);

@@ -127,7 +127,7 @@ __device__ __forceinline__ void epilogue_direct_chunk(const GemmParams& p, int r
         const float4* q4 = reinterpret_cast<const float4*>(p.residual + (size_t)row * p.ldr + col0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            float4 q = q4[j];
+            float4 q = __ldcg(q4 + j);
             r[4 * j + 0] += q.x, r[4 * j + 1] += q.y, r[4 * j + 2] += q.z, r[4 * j + 3] += q.w;
         }
     }
@@ -210,6 +210,8 @@ __device__ __forceinline__ void epilogue_ddpm_chunk(const GemmParams& p, const D
     const float* const xa_add = u.xa_add ? u.xa_add + off0 : nullptr;  // Inpaint model: loop-invariant input offset
     float* const eps_o = (AUX && u.eps_out) ? u.eps_out + off0 : nullptr;
     float* const x0_o = (AUX && u.x0_out) ? u.x0_out + off0 : nullptr;
+    float* const mean_o = (AUX && u.mean_out) ? u.mean_out + off0 : nullptr;
+    float* const raw_o = (AUX && u.raw_x0_out) ? u.raw_x0_out + off0 : nullptr;
     float m = 0.f, f = 0.f;
     const float* sp = nullptr;
     if (INPAINT) {
@@ -225,7 +227,7 @@ __device__ __forceinline__ void epilogue_ddpm_chunk(const GemmParams& p, const D
         for (int i = 0; i < 16; ++i) {
             const int j = h * 16 + i;
             const bool ok = j < ncol;
-            xv[i] = ok ? xp[j * T] : 0.f;
+            xv[i] = ok ? __ldcg(xp + j * T) : 0.f;
             zv[i] = (ok && zp) ? __ldg(zp + j * T) : 0.f;
         }
         float xn[16];
@@ -236,12 +238,14 @@ __device__ __forceinline__ void epilogue_ddpm_chunk(const GemmParams& p, const D
             if (j < ncol) {
                 const float eps = __uint_as_float(v[j]) + __ldg(p.bias + col0 + j);
                 const float sv = INPAINT ? __ldg(sp + j) : 0.f;
-                float x0;
-                const float xnext = ddpm_update_elem(cf, xv[i], eps, zv[i], INPAINT, sv, m, f, u.clip_x0, &x0);
+                float x0, mean, raw;
+                const float xnext = ddpm_update_elem(cf, xv[i], eps, zv[i], INPAINT, sv, m, f, u.clip_x0, &x0, &mean, &raw);
                 xp[j * T] = xnext;
                 if (AUX) {
                     if (eps_o) eps_o[j * T] = eps;
                     if (x0_o) x0_o[j * T] = x0;
+                    if (mean_o) mean_o[j * T] = mean;
+                    if (raw_o) raw_o[j * T] = raw;
                 }
                 xn[i] = xa_add ? xnext + __ldg(xa_add + j * T) : xnext;
             }
@@ -431,10 +435,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const float* tape_t = nullptr;
         bool ddpm_aux = false, ddpm_inpaint = false;
         if (MODE == MODE_DDPM) {
-            t = *p.ddpm.step_ptr;
+            t = load_step(p.ddpm.step_ptr);
             cf = ddpm_load_coefs(p.ddpm, t);
             if (p.ddpm.noise_tape) tape_t = p.ddpm.noise_tape + (size_t)t * p.ddpm.n_clips * p.ddpm.C * p.ddpm.T;
-            ddpm_aux = p.ddpm.eps_out != nullptr || p.ddpm.x0_out != nullptr;
+            ddpm_aux = p.ddpm.eps_out != nullptr || p.ddpm.x0_out != nullptr || p.ddpm.mean_out != nullptr || p.ddpm.raw_x0_out != nullptr;
             ddpm_inpaint = p.ddpm.inpaint_seed != nullptr;
         }
         uint8_t* stg_base = staging + ew * Cfg::STAGING_PER_WARP;
@@ -741,6 +745,7 @@ static int validate_linear(const gd_linear_desc* d) {
 using namespace gd;
 
 extern "C" int gd_linear_bf16(const gd_linear_desc* d, void* stream) {
+    gd::KindScope kind_scope("gemm");
     int rc = validate_linear(d);
     if (rc) return rc;
     if (!d->out_f32 && !d->out_bf16) return set_error(GD_ERR_INVALID, "gd_linear_bf16: no output buffer");
@@ -784,6 +789,7 @@ extern "C" int gd_linear_bf16(const gd_linear_desc* d, void* stream) {
 }
 
 extern "C" int gd_linear_ddpm(const gd_linear_desc* d, const gd_ddpm_desc* u, void* stream) {
+    gd::KindScope kind_scope("ddpm");
     int rc = validate_linear(d);
     if (rc) return rc;
     rc = validate_ddpm(u);
@@ -806,6 +812,7 @@ extern "C" int gd_linear_ddpm(const gd_linear_desc* d, const gd_ddpm_desc* u, vo
 }
 
 extern "C" int gd_conv_taps_bf16(const gd_conv_desc* d, void* stream) {
+    gd::KindScope kind_scope("speech");
     if (!d || !d->in || !d->W || !d->out || !d->scale || !d->shift)
         return set_error(GD_ERR_INVALID, "gd_conv_taps_bf16: null descriptor/operand");
     if (d->n_images <= 0 || d->grid_h <= 0 || d->grid_w <= 0) return set_error(GD_ERR_INVALID, "gd_conv_taps_bf16: empty grid");

@@ -27,6 +27,14 @@ struct LaunchCfg {
     cudaLaunchAttribute attrs[2];
 };
 void fill_launch(LaunchCfg& L, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x = 1);
+// Names the kernel family of the launches issued while it is alive ("gemm", "ddpm", "ln", "attn", "scatter", "step",
+// "pack", "speech"); GD_PDL_OFF=scatter,step (comma list) launches those families WITHOUT programmatic stream
+// serialization - the bisect switch of profiles/determinism_bisect.py.
+struct KindScope {
+    explicit KindScope(const char* kind);
+    ~KindScope();
+    const char* prev;
+};
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,

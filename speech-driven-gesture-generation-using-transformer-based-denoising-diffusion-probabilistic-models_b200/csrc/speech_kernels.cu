@@ -20,10 +20,10 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& q, float (&f)[8]) {
 
 // A feature-map row holds `c` channels as one bf16 plane (split = 0) or as two planes [hi(c) | lo(c)], value = hi + lo.
 __device__ __forceinline__ void load_ch8(const __nv_bfloat16* row, int c, int g, int split, float (&f)[8]) {
-    unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(row) + g), f);
+    unpack_bf16x8(__ldcg(reinterpret_cast<const uint4*>(row) + g), f);  // activations: L2-coherent (common.cuh)
     if (split) {
         float l[8];
-        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(row + c) + g), l);
+        unpack_bf16x8(__ldcg(reinterpret_cast<const uint4*>(row + c) + g), l);
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] += l[j];
     }
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) speech_stem_kernel(const float* __restric
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
                 const int yy = y + ky - 1, xx = x + kx - 1;
-                m[ky * 3 + kx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(base + yy * W + xx) : 0.f;
+                m[ky * 3 + kx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldcg(base + yy * W + xx) : 0.f;
             }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(256) se_residual_relu_kernel(const __nv_bfloat
     float a[8], r[8];
     load_ch8(y + row * ld, c, g, split, a);
     load_ch8(res + row * ld, c, g, split, r);
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + (size_t)img * c) + 2 * g);
-    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + (size_t)img * c) + 2 * g + 1);
+    const float4 g0 = __ldcg(reinterpret_cast<const float4*>(gate + (size_t)img * c) + 2 * g);
+    const float4 g1 = __ldcg(reinterpret_cast<const float4*>(gate + (size_t)img * c) + 2 * g + 1);
     const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
     float o[8];
 #pragma unroll
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(256) pixel_shuffle_rows_kernel(const __nv_bflo
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int ch = g * 8 + k;
-            v[k] = ch < c_real ? __ldg(src + ch * r * r) : (unsigned short)0;
+            v[k] = ch < c_real ? __ldcg(src + ch * r * r) : (unsigned short)0;
         }
         uint4 o;
         o.x = v[0] | ((uint32_t)v[1] << 16), o.y = v[2] | ((uint32_t)v[3] << 16);

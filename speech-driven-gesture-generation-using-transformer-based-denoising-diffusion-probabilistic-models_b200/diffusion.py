@@ -88,8 +88,10 @@ class InpaintBlend:
     update epilogue:  x0 <- (1-f)*m*seed + f*m*x0 + (1-m)*x0  with f the `trans_factor` ramp over frames."""
 
     def __init__(self, seed_poses, masks, trans_factor, pose_seed_len, n_frames):
-        self.seed = seed_poses.float().contiguous()            # (N, T, C)
-        self.mask = masks.float().reshape(masks.shape[0], -1).contiguous()  # (N, T)
+        # chain-owned copies: the engine refreshes these buffers in place when a cached plan is reused, which must never
+        # write through to the caller's inpaint_poses / inpaint_masks tensors
+        self.seed = seed_poses.float().contiguous().clone()            # (N, T, C)
+        self.mask = masks.float().reshape(masks.shape[0], -1).contiguous().clone()  # (N, T)
         if trans_factor is not None:
             assert 0 <= trans_factor <= 1
             assert pose_seed_len is not None, "Provide pose_seed_len when using trans_factor."

@@ -16,6 +16,7 @@ positive `graph_steps` captures that many consecutive steps per graph instead.
 import ctypes as C
 import math
 import os
+import weakref
 
 import torch as th
 
@@ -34,24 +35,25 @@ class PackedWeights:
 
     def __init__(self, model, diffusion, device):
         self.device = device
-        sd = {k: v.detach().to(device=device, dtype=th.float32) for k, v in model.state_dict().items()
+        # repacked on the HOST and uploaded once (a few hundred memcpys instead of ~1000 ATen cast / cat / fill launches)
+        sd = {k: v.detach().to(device="cpu", dtype=th.float32) for k, v in model.state_dict().items()
               if v.dtype.is_floating_point}
         self.kind = model.pose_decoder.kind
         self.d = d = model.d_model
         self.C = model.d_pose
         self.heads = model.pose_decoder.heads
         self.n_layers = model.pose_decoder.n_layers
-        bf = lambda w: w.to(th.bfloat16).contiguous()  # noqa: E731
-        f32 = lambda w: w.float().contiguous()  # noqa: E731
+        bf = lambda w: w.to(th.bfloat16).contiguous().to(device)  # noqa: E731
+        f32 = lambda w: w.float().contiguous().to(device)  # noqa: E731
         pd = "pose_decoder."
         w = sd[pd + "emb_x.weight"]
-        wx = th.zeros(d, _POSE_PAD, device=device)
+        wx = th.zeros(d, _POSE_PAD)
         wx[:, :self.C] = w
         self.embx_w, self.embx_b = bf(wx), f32(sd[pd + "emb_x.bias"])
         self.embm_w, self.embm_b = bf(sd[pd + "emb_mem.weight"]), f32(sd[pd + "emb_mem.bias"])
-        wo = th.zeros(_POSE_PAD, d, device=device)
+        wo = th.zeros(_POSE_PAD, d)
         wo[:self.C] = sd[pd + "out_layers.1.weight"]
-        bo = th.zeros(_POSE_PAD, device=device)
+        bo = th.zeros(_POSE_PAD)
         bo[:self.C] = sd[pd + "out_layers.1.bias"]
         self.out_w, self.out_b = bf(wo), f32(bo)
         self.out_ln = (f32(sd[pd + "out_layers.0.weight"]), f32(sd[pd + "out_layers.0.bias"]))
@@ -97,7 +99,7 @@ class PackedWeights:
         self.pe = positional_table(d, 512).to(device)
         # sinusoidal embedding of the ORIGINAL timestep of every loop index (respace.py:104-113 remap)
         tmap = th.tensor(diffusion.timestep_map, dtype=th.long)
-        self.t_embed = step_embedding_table(d, diffusion.original_num_steps)[tmap].to(device).to(th.bfloat16).contiguous()
+        self.t_embed = step_embedding_table(d, diffusion.original_num_steps)[tmap].to(th.bfloat16).contiguous().to(device)
         self.n_steps = diffusion.num_timesteps
 
 
@@ -163,16 +165,18 @@ class _Launcher:
     def attention(self, n_clips, heads, d_k, q, k, v, out, taps, f32in):
         """q/k/v/out: lists of up to two (tensor_view, rows_per_clip) segments; views start at the right column."""
         a = gd.AttnDesc()
-        for s, (t, rows) in enumerate(q):
+        for s, seg in enumerate(q):  # (view, rows[, rows between clips]): a third entry marks a strided (halo) segment
+            t, rows = seg[0], seg[1]
             a.q[s], a.q_rows[s], a.q_ld[s] = _p(t), rows, t.stride(0)
+            a.q_clip_stride[s] = seg[2] if len(seg) > 2 else 0
         for s, ((tk, rows), (tv, _)) in enumerate(zip(k, v)):
             a.k[s], a.v[s], a.kv_rows[s], a.kv_ld[s] = _p(tk), _p(tv), rows, tk.stride(0)
-        for s, (t, _) in enumerate(out):
+        for s, (t, _) in enumerate(out):  # fewer outputs than query segments: the rest are conv halos (no output rows)
             a.out[s], a.out_ld[s] = _p(t), t.stride(0)
         a.conv_wq, a.conv_bq, a.conv_wk, a.conv_bk, a.conv_wv, a.conv_bv = [_p(t) for t in taps]
         a.n_clips, a.heads, a.d_k, a.scale = n_clips, heads, d_k, 1.0 / math.sqrt(d_k)
         fn = self.lib.gd_dconv_attention_f32in if f32in else self.lib.gd_dconv_attention
-        Lq, Lk, dm, es = sum(r for _, r in q), sum(r for _, r in k), heads * d_k, (4 if f32in else 2)
+        Lq, Lk, dm, es = sum(seg[1] for seg in q[:len(out)]), sum(r for _, r in k), heads * d_k, (4 if f32in else 2)
         flops = n_clips * (4 * Lq * Lk * dm + 6 * dm * (Lq + 2 * Lk))  # QK^T + PV + three 3-tap convs
         nbytes = n_clips * dm * (es * (Lq + 2 * Lk) + 2 * Lq)
         return Op(lambda: gd.check(fn(C.byref(a), self.stream()), "gd_dconv_attention"), "attention", flops, nbytes)
@@ -185,7 +189,9 @@ class SamplingChain:
                  fuse_ln=False, speech_impl="native"):
         if device.type != "cuda":
             raise gd.GdError("the DDPM sampling path runs only on a CUDA device (sm_100a); there is no CPU fallback")
-        self.model, self.diffusion, self.alg = model, diffusion, alg
+        # the model is held weakly: the chain cache must not keep a dropped model (and its tape / graph) alive
+        self._model_ref = weakref.ref(model)
+        self.diffusion, self.alg = diffusion, alg
         self.N, self.C, self.T = shape
         self.device = device
         self.precision = precision
@@ -193,6 +199,8 @@ class SamplingChain:
         # denoise steps per captured CUDA graph; 0 = the whole chain as ONE graph (the default: 1000 steps = ~190 k kernel nodes,
         # captured once per (model, shape) and replayed for every chain)
         self.graph_steps, self.use_graph = (graph_steps if graph_steps and graph_steps > 0 else diffusion.num_timesteps), use_graph
+        if os.environ.get("GD_GRAPH") is not None:  # A/B switch of the determinism harness (profiles/determinism_bisect.py)
+            self.use_graph = bool(int(os.environ["GD_GRAPH"]))
         self.L = _Launcher()
         self.W = model.packed_weights(diffusion, device)
         if self.C != self.W.C:
@@ -204,6 +212,9 @@ class SamplingChain:
         self.xa = th.zeros(self.N * self.T, _POSE_PAD, device=device, dtype=th.bfloat16)
         self.eps = th.zeros_like(self.x)
         self.x0 = th.zeros_like(self.x)
+        self.mean = th.zeros_like(self.x)    # p_mean_variance's `mean` (gaussian_diffusion.py:276-285)
+        self.raw_x0 = th.zeros_like(self.x)  # `raw_x_start`: x0 before denoise_fn (:254)
+        self._var_tabs = None
         self.tape = None
         self.blend = None
         self.xa_add = None  # Inpaint model: (N,C,T) offset added when the bf16 emb_x operand is built
@@ -224,8 +235,16 @@ class SamplingChain:
             raise ValueError(f"speech_impl must be 'native', 'native-bf16' or 'torch', got {self.speech_impl!r}")
         self.native_encoder_chunk = int(env("GD_SPEECH_CHUNK", getattr(model, "native_encoder_chunk", 128)))
         self.graph = None
+        self.graph_info = {}
         self._plan_key = None
         self.Tm = None
+
+    @property
+    def model(self):
+        m = self._model_ref()
+        if m is None:
+            raise gd.GdError("the model of this sampling chain has been garbage-collected")
+        return m
 
     # ------------------------------------------------------------------ loop-invariant conditioning
     def _step_token_table(self):
@@ -319,6 +338,7 @@ class SamplingChain:
         u.step_ptr = _p(self.step)
         u.n_clips, u.C, u.T = self.N, self.C, self.T
         u.eps_out, u.x0_out = _p(self.eps), _p(self.x0)
+        u.mean_out, u.raw_x0_out = _p(self.mean), _p(self.raw_x0)
         u.xa_bf16, u.ld_xa = _p(self.xa), _POSE_PAD
         if self.blend is not None:
             u.inpaint_seed, u.inpaint_mask, u.inpaint_factor = _p(self.blend.seed), _p(self.blend.mask), _p(self.blend.factor)
@@ -410,7 +430,12 @@ class SamplingChain:
                 okw = "out_f32" if self.f32act else "out_bf16"
                 ops.append(L.linear(xn, a["wqkv"], R, 3 * d, d, bias=a["bqkv"], **{okw: qkv}))
                 segs = [(0, T), (Mx, Tm)]
-                qs = [(qkv[lo:, 0:], r) for lo, r in (segs[:1] if last else segs)]
+                qs = [(qkv[lo:, 0:], r) for lo, r in segs]
+                if last:
+                    # only the pose rows are read afterwards (nn.py:445-447), but the symmetric conv3 of the last pose
+                    # frame reaches the first memory row (nn.py:105-113, transformer.py:19-44): memory row 0 of every
+                    # clip rides along as a one-row halo segment without output
+                    qs = [qs[0], (qkv[Mx:, 0:], 1, Tm)]
                 os_ = [(ao[lo:], r) for lo, r in (segs[:1] if last else segs)]
                 ks = [(qkv[lo:, d:], r) for lo, r in segs]
                 vs = [(qkv[lo:, 2 * d:], r) for lo, r in segs]
@@ -497,6 +522,13 @@ class SamplingChain:
                     self.tape.copy_(tp)
                 else:
                     self.tape = tp
+        elif self.alg == "ddim" and getattr(self.model, "match_reference_rng", True):
+            # the reference's ddim_sample draws th.randn_like(x) at every step even though eta = 0 multiplies it away
+            # (gaussian_diffusion.py:475): consume the same draws so that a seeded sequence of calls (generate_sequence
+            # windows, repeated generate_sample) sees the same x_T stream afterwards
+            scratch = th.empty(self.N, self.C, self.T, device=dev)
+            for _ in range(self.n_steps):
+                scratch.normal_()
         blend_key = None if denoise_fn is None else "blend"
         cond = self._conditioning(wav)
         if input_offset is not None:
@@ -528,6 +560,7 @@ class SamplingChain:
         self.x.copy_(x_T.float())
         self._pack_pose_rows()
         self.step.fill_(self.n_steps - 1)
+        self._pos = 0  # steps executed since begin()
 
     def step_eager(self):
         """Enqueue one denoise step.  Concurrent regions fork onto the side stream and join back (inside a capture this
@@ -571,15 +604,39 @@ class SamplingChain:
         th.cuda.current_stream().wait_stream(s)
         th.cuda.synchronize()
         self.x.copy_(saved[0]); self.xa.copy_(saved[1]); self.step.copy_(saved[2])
+        import time
+        free0 = th.cuda.mem_get_info(self.device)[0]
+        t0 = time.perf_counter()
         g = th.cuda.CUDAGraph()
         with th.cuda.graph(g):
             for _ in range(self.graph_steps):
                 self.step_eager()
+        th.cuda.synchronize()
+        t1 = time.perf_counter()
         self.x.copy_(saved[0]); self.xa.copy_(saved[1]); self.step.copy_(saved[2])
         self.graph = g
+        g.replay()  # the first replay uploads the executable graph to the device: count it as part of the one-off cost
+        th.cuda.synchronize()
+        self.x.copy_(saved[0]); self.xa.copy_(saved[1]); self.step.copy_(saved[2])
+        # first-call cost of the public API: capture + instantiate + upload, and what the graph holds
+        self.graph_info = {"steps_per_graph": self.graph_steps, "kernel_nodes": self.graph_steps * len(self.plan),
+                           "capture_s": round(t1 - t0, 3), "first_replay_s": round(time.perf_counter() - t1, 3),
+                           "device_bytes": int(max(free0 - th.cuda.mem_get_info(self.device)[0], 0))}
 
-    def _result(self):
-        return {"sample": self.x, "eps": self.eps, "pred_x_start": self.x0}
+    def _result(self, i=0):
+        """The dict of the step that used loop index `i` (the last executed step), keys as the reference's:
+        p_sample -> sample, mean, variance, log_variance, eps, pred_x_start, raw_x_start (gaussian_diffusion.py:276-285,329);
+        ddim_sample -> sample, pred_x_start (:484)."""
+        if self._var_tabs is None:  # float64 table -> fp32 at the gather, then broadcast (`_extract_into_tensor`, :681-694)
+            d = self.diffusion
+            self._var_tabs = (th.from_numpy(d.posterior_variance).to(self.device).float(),
+                              th.from_numpy(d.posterior_log_variance_clipped).to(self.device).float())
+        var, logvar = (t[i] + th.zeros_like(self.x) for t in self._var_tabs)
+        out = {"sample": self.x, "variance": var, "log_variance": logvar, "eps": self.eps, "pred_x_start": self.x0,
+               "raw_x_start": self.raw_x0}
+        if self.alg == "ddpm":  # the DDIM tables fold the posterior mean away (eta = 0: sample == mean_pred, :476-484)
+            out["mean"] = self.mean
+        return out
 
     def run(self, progress=False, n_steps=None):
         """Run the remaining chain (or `n_steps` steps). Returns the last step's dict."""
@@ -595,20 +652,34 @@ class SamplingChain:
         else:
             for _ in range(total):
                 self.step_eager()
-        return self._result()
+        self._pos += total
+        return self._result(max(self.n_steps - self._pos, 0))
 
     def iterate(self, progress=False):
         """Progressive form (p_sample_loop_progressive): yields cloned per-step dicts."""
-        for _ in range(self.n_steps):
+        for i in range(self.n_steps - 1, -1, -1):
             self.step_eager()
-            yield {k: v.clone() for k, v in self._result().items()}
+            self._pos += 1
+            yield {k: v.clone() for k, v in self._result(i).items()}
 
 
 _CHAINS = {}
 
 
+def release_chains(model=None):
+    """Drop the cached sampling contexts of `model` (all models if None): buffers, noise tapes and captured graphs."""
+    for k in [k for k in _CHAINS if model is None or k[0] == id(model)]:
+        del _CHAINS[k]
+    import gc
+    gc.collect()
+    if th.cuda.is_available():
+        th.cuda.empty_cache()
+
+
 def chain_for(model, diffusion, shape, alg, device, **kw):
-    """Cache of sampling contexts keyed by (model, diffusion, shape, algorithm): buffers and graphs are reused."""
+    """Cache of sampling contexts keyed by (model, diffusion, shape, algorithm): buffers and graphs are reused.  Entries of
+    a model are dropped when the model is garbage-collected, when its weights change (load_state_dict / .to()) and when
+    another batch shape is requested, so the cache holds at most one batch shape per live model."""
     device = th.device(device)
     if device.type == "cuda" and device.index is None:
         device = th.device("cuda", th.cuda.current_device())
@@ -619,8 +690,16 @@ def chain_for(model, diffusion, shape, alg, device, **kw):
     key = (id(model), id(diffusion), shape, alg, str(device), model.weights_version, tuple(sorted(opts.items())))
     ch = _CHAINS.get(key)
     if ch is None:
-        for k in [k for k in _CHAINS if k[0] == id(model) and k[2] != shape]:
-            del _CHAINS[k]  # keep one batch shape per model resident
+        for k in [k for k in _CHAINS if k[0] == id(model) and (k[2] != shape or k[5] != model.weights_version)]:
+            del _CHAINS[k]  # keep one batch shape per model resident; chains of superseded weights are dead
         ch = SamplingChain(model, diffusion, shape, alg, device, **opts)
         _CHAINS[key] = ch
+        if not getattr(model, "_gd_chain_finalizer", False):
+            weakref.finalize(model, release_chains_by_id, id(model))
+            model._gd_chain_finalizer = True
     return ch
+
+
+def release_chains_by_id(model_id):
+    for k in [k for k in _CHAINS if k[0] == model_id]:
+        del _CHAINS[k]

@@ -20,6 +20,7 @@ not depend on its batch.  The mel front end (pre-emphasis, STFT, mel filterbank,
 its own (`gd_mel_power`: one shared-memory fp32 FFT per frame; `gd_instance_norm_rows`); `mel_impl="torch"` evaluates
 `SpeechEncoder.wav2spec` (torch.stft) in fixed micro-batches instead.
 """
+import copy
 import ctypes as C
 import math
 
@@ -32,6 +33,24 @@ PAD = 64  # channel granularity of the convolution GEMM (one 128-byte swizzle ro
 
 def _p(t):
     return None if t is None else t.data_ptr()
+
+
+def _upload(obj, dev, seen):
+    """Move every tensor reachable from the packed-parameter objects (_Conv / _Block / _Head, lists) to `dev`, in place."""
+    if id(obj) in seen:
+        return obj
+    seen.add(id(obj))
+    if isinstance(obj, th.Tensor):
+        return obj.to(dev)
+    if isinstance(obj, list):
+        for i, v in enumerate(obj):
+            obj[i] = _upload(v, dev, seen)
+        return obj
+    if isinstance(obj, (_Conv, _Block, _Head, NativeSpeechEncoder)):
+        for k, v in list(vars(obj).items()):
+            if isinstance(v, (th.Tensor, list, _Conv, _Block, _Head)):
+                setattr(obj, k, _upload(v, dev, seen))
+    return obj
 
 
 def _pad_to(n, m=PAD):
@@ -138,8 +157,12 @@ class NativeSpeechEncoder:
             raise ValueError(f"speech precision must be 'bf16x3' or 'bf16', got {precision!r}")
         if mel_impl not in ("native", "torch"):
             raise ValueError(f"mel_impl must be 'native' or 'torch', got {mel_impl!r}")
-        self.enc, self.L, self.lib, self.dev, self.chunk = enc, launcher, launcher.lib, device, chunk
+        self.L, self.lib, self.dev, self.chunk = launcher, launcher.lib, device, chunk
         self.mel_impl = mel_impl
+        # Pack on the HOST and upload once: the repack is hundreds of tiny casts / pads / fp64 folds, which as ATen
+        # kernels used to be the first ~1000 launches of every process (and hid our kernels from a launch-capped profiler).
+        self.enc = copy.deepcopy(enc).to("cpu")
+        enc = self.enc
         self._pack_front_end()
         self.split = split = int(precision == "bf16x3")
         r = enc.wav_encoder.feat_extractor
@@ -160,6 +183,8 @@ class NativeSpeechEncoder:
         self.heads = [_Head(r.conv_low, r.bn_low, r.fc_low, proj, 1, self.stages[1][0].c, 63, split),
                       _Head(r.conv_mid, r.bn_mid, r.fc_mid, proj, 2, self.shuffle_c, 62, split),
                       _Head(r.conv_high, r.bn_high, r.fc_high, proj, 4, self.shuffle_c, 62, split)]
+        _upload(self, th.device(device), set())
+        self.enc = enc if mel_impl == "native" else self.enc.to(device)  # the torch mel front end runs the module itself
         self._ws = {}
 
     def _pack_front_end(self):

@@ -208,3 +208,44 @@ def test_eval_infer_time_ddim():
     for alg in ("ddim", "ddpm"):
         mean_ms, std_ms = gen.eval_infer_time_ddim((N, C, T), kw, sample_alg=alg, repetitions=3, device="cuda")
         assert 0 < mean_ms < 5e3 and std_ms >= 0
+
+
+def test_p_sample_dict_has_every_reference_key():
+    """p_sample_loop(_progressive) hands back the reference's whole dict (gaussian_diffusion.py:276-285,329): sample, mean,
+    variance, log_variance, eps, pred_x_start, raw_x_start - with an in-paint blend so raw_x_start != pred_x_start."""
+    import numpy as np
+    from gesture_b200.diffusion import InpaintBlend
+    N = 2
+    model, diffusion, C, T, L, params = build("beat", "boost", respacing="ddim10", device="cuda")
+    wav = synthetic_wav(N, L, seed=21)
+    x_T, tape = noise_tape((N, C, T), 10, seed=22)
+    seed = th.randn(N, T, C, generator=th.Generator().manual_seed(23))
+    masks = th.ones(N, T, 1)
+    masks[:, 10:] = 0
+    blend = InpaintBlend(seed.cuda(), masks.cuda(), 0.575, 10, T)
+    keys = {"sample", "mean", "variance", "log_variance", "eps", "pred_x_start", "raw_x_start"}
+    x_prev = x_T.cuda()
+    A = th.from_numpy(diffusion.sqrt_recip_alphas_cumprod).float()
+    B = th.from_numpy(diffusion.sqrt_recipm1_alphas_cumprod).float()
+    steps = list(diffusion.p_sample_loop_progressive(model, (N, C, T), noise=x_T, model_kwargs={"wav": wav}, denoise_fn=blend,
+                                                     device="cuda", noise_tape=tape))
+    assert len(steps) == 10
+    for k, out in enumerate(steps):
+        i = 9 - k
+        assert set(out) == keys
+        var = np.float32(diffusion.posterior_variance[i])
+        logvar = np.float32(diffusion.posterior_log_variance_clipped[i])
+        assert th.equal(out["variance"], th.full_like(out["sample"], float(var)))
+        assert th.equal(out["log_variance"], th.full_like(out["sample"], float(logvar)))
+        raw = A[i] * x_prev - B[i] * out["eps"]                      # _predict_xstart_from_eps (:287-292)
+        assert th.equal(out["raw_x_start"], raw)
+        assert th.equal(out["pred_x_start"], blend(out["raw_x_start"]))  # denoise_fn (generator.py:271-280)
+        c1 = float(np.float32(diffusion.posterior_mean_coef1[i])), float(np.float32(diffusion.posterior_mean_coef2[i]))
+        assert th.equal(out["mean"], c1[0] * out["pred_x_start"] + c1[1] * x_prev)
+        sig = th.exp(0.5 * th.tensor(float(logvar)))
+        expect = out["mean"] + (sig * tape[k].cuda() if i != 0 else 0.0)
+        assert th.equal(out["sample"], expect)
+        x_prev = out["sample"]
+    last = diffusion.p_sample_loop(model, (N, C, T), noise=x_T, model_kwargs={"wav": wav}, denoise_fn=blend, device="cuda",
+                                   noise_tape=tape)
+    assert set(last) == keys and th.equal(last["sample"], steps[-1]["sample"]) and th.equal(last["mean"], steps[-1]["mean"])

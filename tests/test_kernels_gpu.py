@@ -233,6 +233,45 @@ def _dconv_attention_case(gd, dk, rows_q, rows_kv, f32, N):
     assert (got - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item())
 
 
+
+@pytest.mark.parametrize("f32,N", [(False, 5), (False, 300), (True, 5)])
+def test_dconv_attention_query_halo(gd, f32, N):
+    """Last tedexp layer (nn.py:105-113, 445-447): outputs for the 34 pose queries only, but the depth-wise conv3 of
+    pose frame 33 reaches memory row 0 - it rides along as a one-row, strided, output-less query segment (ABI 4).  The
+    reference is the conv over the FULL [x ; memory] query sequence, sliced to the first 34 rows; the last frame is
+    checked on its own (dropping the seam tap hid under whole-tensor tolerances)."""
+    H, dk, Tx, Tm = 8, 64, 34, 104
+    d_model = H * dk
+    g = torch.Generator(device="cuda").manual_seed(11)
+    dt = torch.float32 if f32 else torch.bfloat16
+    es = 4 if f32 else 2
+    xs = torch.randn(N * Tx, 3 * d_model, device="cuda", generator=g).to(dt)
+    ms = torch.randn(N * Tm, 3 * d_model, device="cuda", generator=g).to(dt)
+    taps = [torch.randn(dk, 3, device="cuda", generator=g) * 0.5 if i % 2 == 0 else torch.randn(dk, device="cuda", generator=g) * 0.1 for i in range(6)]
+    out = torch.zeros(N * Tx, d_model, device="cuda", dtype=torch.bfloat16)
+    a = gd.AttnDesc()
+    a.q[0], a.q_rows[0], a.q_ld[0] = xs.data_ptr(), Tx, 3 * d_model
+    a.q[1], a.q_rows[1], a.q_ld[1], a.q_clip_stride[1] = ms.data_ptr(), 1, 3 * d_model, Tm
+    a.out[0], a.out_ld[0] = out.data_ptr(), d_model
+    for s, (sg, r) in enumerate(((xs, Tx), (ms, Tm))):
+        a.k[s], a.v[s] = sg.data_ptr() + d_model * es, sg.data_ptr() + 2 * d_model * es
+        a.kv_rows[s], a.kv_ld[s] = r, 3 * d_model
+    a.conv_wq, a.conv_bq, a.conv_wk, a.conv_bk, a.conv_wv, a.conv_bv = [t.data_ptr() for t in taps]
+    a.n_clips, a.heads, a.d_k, a.scale = N, H, dk, 1.0 / math.sqrt(dk)
+    fn = gd.load().gd_dconv_attention_f32in if f32 else gd.load().gd_dconv_attention
+    gd.check(fn(C.byref(a), _stream()))
+    torch.cuda.synchronize()
+    joint = torch.cat([xs.float().view(N, Tx, -1), ms.float().view(N, Tm, -1)], dim=1)
+    part = lambda lo: joint[:, :, lo:lo + d_model].reshape(N, Tx + Tm, H, dk)  # noqa: E731
+    ref = _ref_attention(part(0), part(d_model), part(2 * d_model), taps, a.scale).reshape(N, Tx + Tm, d_model)[:, :Tx]
+    got = out.view(N, Tx, d_model).float()
+    tol = 3e-2 * max(1.0, ref.abs().max().item())
+    assert (got - ref).abs().max().item() < tol
+    assert (got[:, -1] - ref[:, -1]).abs().max().item() < tol
+    # and the seam tap matters: without it the last frame is far outside the tolerance
+    nohalo = _ref_attention(part(0)[:, :Tx], part(d_model), part(2 * d_model), taps, a.scale).reshape(N, Tx, d_model)
+    assert (nohalo[:, -1] - ref[:, -1]).abs().max().item() > 3 * tol
+
 def _tables(n=1000):
     g = torch.Generator().manual_seed(3)
     return [torch.rand(n, generator=g).cuda() + 0.5 for _ in range(5)]
