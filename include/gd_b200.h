@@ -117,6 +117,9 @@ typedef struct gd_ddpm_desc {
                                  adds to its input (models/model.py:155-166)                                        */
     float* mean_out;          /* ABI 4, optional (N, C, T): posterior mean (`mean` of p_mean_variance, :276-285)      */
     float* raw_x0_out;        /* ABI 4, optional (N, C, T): x0 BEFORE the in-paint blend (`raw_x_start`, :254)        */
+    const int32_t* aux_step_ptr; /* ABI 4, optional device int: when non-NULL and >= 0, the four optional outputs
+                                 (eps_out, x0_out, mean_out, raw_x0_out) are written ONLY in the step whose t equals it
+                                 (a whole-chain graph needs them for its last step only); NULL or < 0: every step       */
 } gd_ddpm_desc;
 
 /* Standalone update from an eps tensor laid out (N, C, T). */
@@ -158,6 +161,18 @@ typedef struct gd_ln_desc {
 } gd_ln_desc;
 
 int gd_linear_resid_ln(const gd_linear_desc* d, const gd_ln_desc* ln, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * gd_linear_ln_bf16 (ABI 4): LayerNorm as the PROLOGUE of the GEMM that consumes it,
+ *
+ *     out_bf16 = act( LayerNorm(H; gamma, beta, eps) · Wᵀ + bias )
+ *
+ * Replaces `self.norm_*(x)` + the fused Q|K|V projection / the first FeedForward layer (models/nn.py:97-124,158-173 ->
+ * transformer.py:51,57,146-152).  d->A is the fp32 residual stream H [M, K] (row stride d->lda in fp32 elements), K must be
+ * the model width (256 or 512), N a multiple of 128; bias required; bf16 output only.  The normalised rows are produced
+ * inside the kernel, bit-identical to gd_layernorm, and never reach HBM.
+ * ------------------------------------------------------------------------------------------ */
+int gd_linear_ln_bf16(const gd_linear_desc* d, const float* gamma, const float* beta, float eps, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * gd_dconv_attention: MultiDConvHeadAttention core (models/modules/transformer.py:88-126):

@@ -25,7 +25,7 @@ class DdpmDesc(C.Structure):
                 ("coef_C2", c_vp), ("sigma", c_vp), ("step_ptr", c_vp), ("n_clips", c_i32), ("C", c_i32),
                 ("T", c_i32), ("eps_out", c_vp), ("x0_out", c_vp), ("xa_bf16", c_vp), ("ld_xa", c_i32),
                 ("inpaint_seed", c_vp), ("inpaint_mask", c_vp), ("inpaint_factor", c_vp), ("clip_x0", c_f32),
-                ("xa_add", c_vp), ("mean_out", c_vp), ("raw_x0_out", c_vp)]
+                ("xa_add", c_vp), ("mean_out", c_vp), ("raw_x0_out", c_vp), ("aux_step_ptr", c_vp)]
 
 
 class LnDesc(C.Structure):
@@ -62,6 +62,7 @@ SYMBOLS = {
     "gd_ddpm_update": (c_i32, [C.POINTER(DdpmDesc), c_vp, c_vp]),
     "gd_linear_ddpm": (c_i32, [C.POINTER(LinearDesc), C.POINTER(DdpmDesc), c_vp]),
     "gd_linear_resid_ln": (c_i32, [C.POINTER(LinearDesc), C.POINTER(LnDesc), c_vp]),
+    "gd_linear_ln_bf16": (c_i32, [C.POINTER(LinearDesc), c_vp, c_vp, c_f32, c_vp]),
     "gd_layernorm": (c_i32, [c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_f32, c_vp]),
     "gd_dconv_attention": (c_i32, [C.POINTER(AttnDesc), c_vp]),
     "gd_dconv_attention_f32in": (c_i32, [C.POINTER(AttnDesc), c_vp]),

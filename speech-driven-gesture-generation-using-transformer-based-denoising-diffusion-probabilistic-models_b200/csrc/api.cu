@@ -30,19 +30,30 @@ PFN_encodeTiled get_encode_tiled() {
     return reinterpret_cast<PFN_encodeTiled>(fn);
 }
 
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return dev < GD_MAX_DEVICES ? dev : GD_MAX_DEVICES - 1;
+}
+
 int sm_count() {
-    static int n = 0;
+    static int n_dev[GD_MAX_DEVICES] = {};
+    int& n = n_dev[current_device()];
     if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, current_device());
         if (n <= 0) n = 148;
     }
     return n;
 }
 
 int check_device() {
-    static int ok = -1;
+    static int ok_dev[GD_MAX_DEVICES];
+    static bool init = false;
+    if (!init) {
+        for (int i = 0; i < GD_MAX_DEVICES; ++i) ok_dev[i] = -1;
+        init = true;
+    }
+    int& ok = ok_dev[current_device()];
     if (ok < 0) {
         int dev = 0, major = 0;
         if (cudaGetDevice(&dev) != cudaSuccess ||

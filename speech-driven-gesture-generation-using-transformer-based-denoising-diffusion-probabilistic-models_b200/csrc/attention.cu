@@ -261,7 +261,8 @@ template <typename T, int DK, int KB>
 static int launch_attention(const AttnParams& p, int n_clips, cudaStream_t s) {
     const int Lq_pad = (p.Lq + 15) & ~15;
     const size_t smem = (size_t)(Lq_pad + 2 * KB * 16) * (DK + 8) * 2 + 3 * DK * 4 * sizeof(float);
-    static size_t configured = 0;
+    static size_t configured_dev[GD_MAX_DEVICES] = {};  // function attributes are per device
+    size_t& configured = configured_dev[current_device()];
     if (smem > configured) {
         const size_t want = smem > 48 * 1024 ? smem : 48 * 1024;
         GD_CUDA_CHECK(cudaFuncSetAttribute(dconv_attention_kernel<T, DK, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -591,7 +592,11 @@ static bool conv_in_bf16() {
 template <int DK, int KB, bool CONV_BF16>
 static int launch_attention_tma(const AttnParams& p, int n_clips, cudaStream_t s) {
     constexpr int HG = 64 / DK;
-    constexpr int MAXT = 256;  // 8 warps x 128 registers: two CTAs fill the register file of an SM exactly
+    // 8 warps x 128 registers: two CTAs fill the register file of an SM exactly.  (Round 2, measured and reverted: 9 warps x 112
+    // registers for the 138-token joint attention - nine 16-query tiles, so on 8 warps the second MMA round runs one warp out
+    // of eight - was SLOWER in the chain: attention 1.45 -> 1.60 ms per tedexp step; 40 bytes of spill and 18 instead of 16
+    // warps fighting for the same issue slots cost more than the idle round.)
+    constexpr int MAXT = 256;
     constexpr int MAXREG = KB <= 5 ? 96 : 128;  // short key ranges need fewer registers: 20 instead of 16 warps per SM
     auto kern = dconv_attention_tma_kernel<DK, KB, MAXT, MAXREG, CONV_BF16>;
     const int Lq_pad = (p.Lq + 15) & ~15, Lk_pad = KB * 16;
@@ -628,7 +633,8 @@ static int launch_attention_tma(const AttnParams& p, int n_clips, cudaStream_t s
                             (uint64_t)p.heads * DK, p.kv_ld[has_k ? sgi : 0], p.kv_rows[has_k ? sgi : 0]);
         if (rc) return rc;
     }
-    static size_t configured = 0;
+    static size_t configured_dev[GD_MAX_DEVICES] = {};  // function attributes are per device
+    size_t& configured = configured_dev[current_device()];
     if (smem > configured) {
         GD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
         GD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

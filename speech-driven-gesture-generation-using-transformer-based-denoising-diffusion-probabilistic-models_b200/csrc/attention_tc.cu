@@ -558,7 +558,8 @@ int launch_attention_tc(const AttnParams& p, int n_clips, cudaStream_t s) {
                             (uint64_t)p.heads * 64, p.kv_ld[has_k ? sgi : 0], p.kv_rows[has_k ? sgi : 0]);
         if (rc) return rc;
     }
-    static size_t configured = 0;
+    static size_t configured_dev[GD_MAX_DEVICES] = {};  // function attributes are per device
+    size_t& configured = configured_dev[current_device()];
     if (smem > configured) {
         GD_CUDA_CHECK(cudaFuncSetAttribute(dconv_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)(smem > 48 * 1024 ? smem : 48 * 1024)));

@@ -6,7 +6,7 @@ import sys
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["api.cu", "gemm_tcgen05.cu", "gemm_resid_ln.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "speech_kernels.cu"]
+SOURCES = ["api.cu", "gemm_tcgen05.cu", "gemm_resid_ln.cu", "gemm_ln_a.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "speech_kernels.cu"]
 OUT = os.path.join(os.path.dirname(HERE), "libgd_b200.so")
 OBJ_DIR = os.path.join(HERE, "_obj")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--compiler-options", "-fPIC"]

@@ -236,4 +236,31 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// ---------------------------------------------------------------- LayerNorm row arithmetic
+// Shared by layernorm_rows_kernel (elementwise.cu) and the LayerNorm prologue of gemm_ln_a_kernel (gemm_ln_a.cu): lane l of
+// a warp holds float4 number (i*32 + l) of the row, i = 0..V-1 (V = D/128).  Same lane->column map, same reduction tree and
+// explicitly rounded operations in both kernels, so the two plans produce the same bf16 rows bit for bit.
+template <int V>
+__device__ __forceinline__ void ln_row_stats(const float4 (&v)[V], float eps, float& mean, float& rstd) {
+    constexpr float inv_d = 1.0f / (V * 128);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) s = __fadd_rn(s, __fadd_rn(__fadd_rn(v[i].x, v[i].y), __fadd_rn(v[i].z, v[i].w)));
+    mean = __fmul_rn(warp_sum(s), inv_d);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const float a = __fsub_rn(v[i].x, mean), b = __fsub_rn(v[i].y, mean), c = __fsub_rn(v[i].z, mean), d = __fsub_rn(v[i].w, mean);
+        q = __fadd_rn(q, __fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fadd_rn(__fmul_rn(c, c), __fmul_rn(d, d))));
+    }
+    rstd = rsqrtf(__fadd_rn(__fmul_rn(warp_sum(q), inv_d), eps));
+}
+// (x - mean) * rstd * gamma + beta for one float4 -> 4 bf16 (8 bytes)
+__device__ __forceinline__ uint2 ln_apply_pack(const float4& x, float mean, float rstd, const float4& g, const float4& b) {
+    uint2 w;
+    w.x = pack_bf16x2(__fmaf_rn(__fmul_rn(__fsub_rn(x.x, mean), rstd), g.x, b.x), __fmaf_rn(__fmul_rn(__fsub_rn(x.y, mean), rstd), g.y, b.y));
+    w.y = pack_bf16x2(__fmaf_rn(__fmul_rn(__fsub_rn(x.z, mean), rstd), g.z, b.z), __fmaf_rn(__fmul_rn(__fsub_rn(x.w, mean), rstd), g.w, b.w));
+    return w;
+}
+
 }  // namespace gd

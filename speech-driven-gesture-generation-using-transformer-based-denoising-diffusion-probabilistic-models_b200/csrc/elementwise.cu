@@ -36,27 +36,13 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
     const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < V; ++i) s += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
-        const float mean = warp_sum(s) * (1.0f / D);
-        float q = 0.f;
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-            const float a = v[r][i].x - mean, b = v[r][i].y - mean, c = v[r][i].z - mean, d = v[r][i].w - mean;
-            q += (a * a + b * b) + (c * c + d * d);
-        }
-        const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+        float mean, rstd;
+        ln_row_stats<V>(v[r], eps, mean, rstd);
         if (row0 + r < M) {
             uint2* orow = reinterpret_cast<uint2*>(out + (size_t)(row0 + r) * ldo);
 #pragma unroll
-            for (int i = 0; i < V; ++i) {
-                const float4 g = __ldg(g4 + i * 32 + lane), b = __ldg(b4 + i * 32 + lane);
-                uint2 w;
-                w.x = pack_bf16x2((v[r][i].x - mean) * rstd * g.x + b.x, (v[r][i].y - mean) * rstd * g.y + b.y);
-                w.y = pack_bf16x2((v[r][i].z - mean) * rstd * g.z + b.z, (v[r][i].w - mean) * rstd * g.w + b.w);
-                orow[i * 32 + lane] = w;
-            }
+            for (int i = 0; i < V; ++i)
+                orow[i * 32 + lane] = ln_apply_pack(v[r][i], mean, rstd, __ldg(g4 + i * 32 + lane), __ldg(b4 + i * 32 + lane));
         }
     }
 }
@@ -73,6 +59,11 @@ __global__ void __launch_bounds__(256) ddpm_update_kernel(const gd_ddpm_desc u, 
     const size_t total = (size_t)u.n_clips * c_span * u.T;
     const size_t tape_base = (size_t)t * u.n_clips * u.C * u.T;
     const bool inpaint = u.inpaint_seed != nullptr;
+    bool aux = true;
+    if (u.aux_step_ptr) {
+        const int aux_t = load_step(u.aux_step_ptr);
+        aux = aux_t < 0 || aux_t == t;
+    }
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int frame = (int)(i % u.T);
         const int c = (int)((i / u.T) % c_span);
@@ -92,10 +83,12 @@ __global__ void __launch_bounds__(256) ddpm_update_kernel(const gd_ddpm_desc u, 
             float x0, mean, raw;
             xnext = ddpm_update_elem(cf, __ldcg(u.x + idx), e, z, inpaint, seed, m, f, u.clip_x0, &x0, &mean, &raw);
             u.x[idx] = xnext;
-            if (u.eps_out) u.eps_out[idx] = e;
-            if (u.x0_out) u.x0_out[idx] = x0;
-            if (u.mean_out) u.mean_out[idx] = mean;
-            if (u.raw_x0_out) u.raw_x0_out[idx] = raw;
+            if (aux) {
+                if (u.eps_out) u.eps_out[idx] = e;
+                if (u.x0_out) u.x0_out[idx] = x0;
+                if (u.mean_out) u.mean_out[idx] = mean;
+                if (u.raw_x0_out) u.raw_x0_out[idx] = raw;
+            }
         }
         if (u.xa_bf16)
             reinterpret_cast<__nv_bfloat16*>(u.xa_bf16)[((size_t)clip * u.T + frame) * u.ld_xa + c] =

@@ -393,11 +393,12 @@ static int launch_resid_ln(const gd_linear_desc* d, const gd_ln_desc* ln, cudaSt
     rc = make_tmap_2d(&tpf, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d->out_f32, d->M, d->N, d->ldo_f32, RL_BN, RL_BLOCK_M,
                       CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[GD_MAX_DEVICES] = {};  // function attributes are per device
+    const int dev_idx = current_device();
+    if (!attr_set[dev_idx]) {
         GD_CUDA_CHECK(cudaFuncSetAttribute(gemm_resid_ln_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            RL_SMEM_BYTES));
-        attr_set = true;
+        attr_set[dev_idx] = true;
     }
     ResidLnParams p{};
     p.M = d->M, p.N = d->N, p.K = d->K, p.bias = d->bias;

@@ -97,6 +97,17 @@ __device__ __forceinline__ void add_bias_chunk(float (&r)[32], const uint32_t (&
     }
 }
 
+// Positional row bias of the TMA epilogues: r[j] += rowbias[(row % period + offset) * N + col0 + j]  (emb_x / emb_mem + PE)
+__device__ __forceinline__ void add_rowbias_chunk(float (&r)[32], const GemmParams& p, int row, int col0) {
+    const int pos = (row % p.rowbias_period) + p.rowbias_offset;
+    const float4* b4 = reinterpret_cast<const float4*>(p.rowbias + (size_t)pos * p.N + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 b = __ldg(b4 + j);
+        r[4 * j + 0] += b.x, r[4 * j + 1] += b.y, r[4 * j + 2] += b.z, r[4 * j + 3] += b.w;
+    }
+}
+
 // MODE_DIRECT: one thread = one output row, 32 consecutive columns starting at col0, every epilogue feature.
 __device__ __forceinline__ void epilogue_direct_chunk(const GemmParams& p, int row, int col0, uint32_t (&v)[32]) {
     float r[32];
@@ -439,6 +450,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             cf = ddpm_load_coefs(p.ddpm, t);
             if (p.ddpm.noise_tape) tape_t = p.ddpm.noise_tape + (size_t)t * p.ddpm.n_clips * p.ddpm.C * p.ddpm.T;
             ddpm_aux = p.ddpm.eps_out != nullptr || p.ddpm.x0_out != nullptr || p.ddpm.mean_out != nullptr || p.ddpm.raw_x0_out != nullptr;
+            if (ddpm_aux && p.ddpm.aux_step_ptr) {  // optional outputs only in the step that asks for them
+                const int aux_t = load_step(p.ddpm.aux_step_ptr);
+                ddpm_aux = aux_t < 0 || aux_t == t;
+            }
             ddpm_inpaint = p.ddpm.inpaint_seed != nullptr;
         }
         uint8_t* stg_base = staging + ew * Cfg::STAGING_PER_WARP;
@@ -506,6 +521,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         }
                         float r[32];
                         add_bias_chunk(r, *reinterpret_cast<const uint32_t(*)[32]>(&v[32 * h]), b, has_bias);
+                        if (p.rowbias) add_rowbias_chunk(r, p, row, col0 + h * 32);
                         if (p.act == GD_ACT_RELU2) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
@@ -555,6 +571,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (c == WCOLS / 32 - 1) release_accumulator();
                     float r[32];
                     add_bias_chunk(r, v, b, has_bias);
+                    if (p.rowbias) add_rowbias_chunk(r, p, row, col0);
                     if (p.act == GD_ACT_RELU2) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
@@ -669,11 +686,12 @@ static int launch_gemm_cl(const GemmParams& p, const void* A, int lda, const voi
         rc = make_tmap_2d(&tout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.out_f32, p.M, p.N, p.ldo_f32, 32, 32,
                           CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[GD_MAX_DEVICES] = {};  // function attributes are per device
+    const int dev_idx = current_device();
+    if (!attr_set[dev_idx]) {
         GD_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, MODE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::SMEM_BYTES));
-        attr_set = true;
+        attr_set[dev_idx] = true;
     }
     const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
     const int work = ((m_tiles + CL - 1) / CL) * (p.N / BN);  // cluster-level work items
@@ -714,11 +732,12 @@ static int launch_conv(const GemmParams& p, const void* A, int c_in, const void*
     if (rc) return rc;
     rc = make_tmap_2d_bf16(&tb, W, p.N, p.K, p.K, BN);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[GD_MAX_DEVICES] = {};  // function attributes are per device
+    const int dev_idx = current_device();
+    if (!attr_set[dev_idx]) {
         GD_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::SMEM_BYTES));
-        attr_set = true;
+        attr_set[dev_idx] = true;
     }
     const int work = ((p.M + BLOCK_M - 1) / BLOCK_M) * (p.N / BN);
     const int grid = work < sm_count() ? work : sm_count();
@@ -766,7 +785,7 @@ extern "C" int gd_linear_bf16(const gd_linear_desc* d, void* stream) {
     // epilogue flavour: TMA stores for the two hot shapes, the per-row path for everything else
     int mode = MODE_DIRECT;
     const bool aligned16 = ((reinterpret_cast<uintptr_t>(d->out_f32) | reinterpret_cast<uintptr_t>(d->out_bf16)) & 15) == 0;
-    if (!d->rowbias && aligned16) {
+    if (aligned16) {  // (the positional rowbias is supported by the TMA epilogues too)
         if (d->out_bf16 && !d->out_f32 && !d->residual)
             mode = MODE_TMA_BF16;
         else if (d->out_f32 && !d->out_bf16 && (!d->residual || (d->residual == d->out_f32 && d->ldr == d->ldo_f32))) {

@@ -12,7 +12,9 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 int set_error(int code, const char* fmt, ...);  // returns code
 PFN_encodeTiled get_encode_tiled();             // resolved through cudaGetDriverEntryPoint (no -lcuda link)
-int sm_count();                                 // SMs of the current device (148 on B200)
+constexpr int GD_MAX_DEVICES = 64;
+int current_device();                           // cudaGetDevice(), clamped to [0, GD_MAX_DEVICES)
+int sm_count();                                 // SMs of the current device (148 on B200), cached per device
 int check_device();                             // GD_OK iff current device is compute capability 10.x
 void count_launch();
 int validate_ddpm(const gd_ddpm_desc* u);

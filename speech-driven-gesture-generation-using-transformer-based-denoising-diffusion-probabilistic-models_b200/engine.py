@@ -157,6 +157,16 @@ class _Launcher:
         return Op(lambda: gd.check(lib.gd_linear_resid_ln(C.byref(d), C.byref(l), self.stream()), "gd_linear_resid_ln"),
                   "gemm_ln", 2 * M * N * K + 8 * M * N, nbytes)
 
+    def linear_ln(self, H, ln, W, M, N, K, bias, act=gd.ACT_NONE, out_bf16=None):
+        """out = act(LayerNorm(H; ln)·Wᵀ + bias) in one launch (gd_linear_ln_bf16): H fp32 rows, bf16 out."""
+        d = gd.LinearDesc()
+        d.A, d.W, d.M, d.N, d.K, d.lda, d.ldw = _p(H), _p(W), M, N, K, H.stride(0), W.stride(0)
+        d.bias, d.act, d.out_bf16, d.ldo_bf16 = _p(bias), act, _p(out_bf16), out_bf16.stride(0)
+        lib, g, b = self.lib, ln[0], ln[1]
+        nbytes = 4 * M * K + 2 * N * K + 2 * M * N
+        return Op(lambda: gd.check(lib.gd_linear_ln_bf16(C.byref(d), _p(g), _p(b), 1e-5, self.stream()), "gd_linear_ln_bf16"),
+                  "gemm", 2 * M * N * K, nbytes)
+
     def layernorm(self, x, gamma_beta, out, M, D):
         lib, g, b = self.lib, gamma_beta[0], gamma_beta[1]
         args = (_p(x), x.stride(0), _p(g), _p(b), _p(out), out.stride(0), M, D, 1e-5)
@@ -186,7 +196,7 @@ class SamplingChain:
     """One (model, diffusion, batch shape, algorithm) sampling context: buffers + plan + captured graph."""
 
     def __init__(self, model, diffusion, shape, alg, device, precision="bf16", graph_steps=1, use_graph=True,
-                 fuse_ln=False, speech_impl="native"):
+                 fuse_ln=False, speech_impl="native", ln_prologue=False):
         if device.type != "cuda":
             raise gd.GdError("the DDPM sampling path runs only on a CUDA device (sm_100a); there is no CPU fallback")
         # the model is held weakly: the chain cache must not keep a dropped model (and its tape / graph) alive
@@ -208,6 +218,9 @@ class SamplingChain:
         self.n_steps = diffusion.num_timesteps
         self.tabs = [t.to(device).contiguous() for t in diffusion.step_tables(alg)]
         self.step = th.zeros(1, dtype=th.int32, device=device)
+        # loop index whose step writes the optional outputs (eps / x0 / mean / raw_x0); -1 = every step.  A chain replay
+        # needs them for its last step only: 4 x (N,C,T) fp32 stores saved in each of the other 999 steps.
+        self.aux_step = th.full((1,), -1, dtype=th.int32, device=device)
         self.x = th.zeros(self.N, self.C, self.T, device=device)
         self.xa = th.zeros(self.N * self.T, _POSE_PAD, device=device, dtype=th.bfloat16)
         self.eps = th.zeros_like(self.x)
@@ -226,6 +239,10 @@ class SamplingChain:
         # the captured chain it loses to the two-kernel form (tedexp 5.44 vs 5.28 ms/step, beat 1.09 vs 1.04) although
         # its kernels sum to less - the stand-alone LayerNorm overlaps with its neighbours, the cluster kernel does not.
         self.fuse_ln = bool(int(env("GD_FUSE_LN", int(fuse_ln))))
+        # LayerNorm as the prologue of the consuming GEMM (gd_linear_ln_bf16): no stand-alone LayerNorm launches except the
+        # last one (out_layers.0).  bf16 plans only (the fp32-activation parity path keeps fp32 Q|K|V rows).
+        self.ln_prologue = bool(int(env("GD_LN_PROLOGUE", int(ln_prologue)))) and not self.f32act \
+            and not self.fuse_ln
         self.encoder_chunk = getattr(model, "encoder_chunk", 16)
         # once-per-clip speech encoder: "native" = ResNetSE-34 on our tensor-core convolutions in split precision (bf16x3:
         # fp32-class products), "native-bf16" = the same with plain bf16 feature maps (faster, ~1e-2 feature error that a
@@ -339,6 +356,7 @@ class SamplingChain:
         u.n_clips, u.C, u.T = self.N, self.C, self.T
         u.eps_out, u.x0_out = _p(self.eps), _p(self.x0)
         u.mean_out, u.raw_x0_out = _p(self.mean), _p(self.raw_x0)
+        u.aux_step_ptr = _p(self.aux_step)
         u.xa_bf16, u.ld_xa = _p(self.xa), _POSE_PAD
         if self.blend is not None:
             u.inpaint_seed, u.inpaint_mask, u.inpaint_factor = _p(self.blend.seed), _p(self.blend.mask), _p(self.blend.factor)
@@ -346,13 +364,18 @@ class SamplingChain:
         u.xa_add = _p(self.xa_add)
         return u
 
-    def _attn_block(self, ops, a, rows_lo, rows_hi, segs, xn, qkv, ao, H, n_heads, next_ln=None):
+    def _attn_block(self, ops, a, rows_lo, rows_hi, segs, xn, qkv, ao, H, n_heads, next_ln=None, ln_in=None):
         """LN'd rows [lo,hi) -> fused QKV GEMM -> dconv attention over `segs` -> out-proj + residual into H
-        (+ the LayerNorm that follows, `next_ln`, written to the same rows of xn)."""
+        (+ the LayerNorm that follows, `next_ln`, written to the same rows of xn).  With the LayerNorm-prologue plan the
+        QKV GEMM normalises H itself with `ln_in` and no LayerNorm follows."""
         d, L = self.W.d, self.L
         M = rows_hi - rows_lo
         okw = "out_f32" if self.f32act else "out_bf16"
-        ops.append(L.linear(xn[rows_lo:rows_hi], a["wqkv"], M, 3 * d, d, bias=a["bqkv"], **{okw: qkv[rows_lo:rows_hi]}))
+        if self.ln_prologue:
+            ops.append(L.linear_ln(H[rows_lo:rows_hi], ln_in, a["wqkv"], M, 3 * d, d, a["bqkv"], out_bf16=qkv[rows_lo:rows_hi]))
+            next_ln = None
+        else:
+            ops.append(L.linear(xn[rows_lo:rows_hi], a["wqkv"], M, 3 * d, d, bias=a["bqkv"], **{okw: qkv[rows_lo:rows_hi]}))
         q = [(qkv[lo:, 0:], r) for lo, r in segs]
         k = [(qkv[lo:, d:], r) for lo, r in segs]
         v = [(qkv[lo:, 2 * d:], r) for lo, r in segs]
@@ -374,11 +397,16 @@ class SamplingChain:
                 ops.append(L.layernorm(H[:split], ln, xn[:split], split, d))
                 ops.append(L.layernorm(H[split:], ln2, xn[split:], M - split, d))
 
-    def _ffn_block(self, ops, f, lo, hi, xn, hid, H, next_ln=None):
-        """xn rows [lo,hi) already hold LN(H): up-projection + ReLU², down-projection + residual (+ the next LayerNorm)."""
+    def _ffn_block(self, ops, f, lo, hi, xn, hid, H, next_ln=None, ln_in=None):
+        """xn rows [lo,hi) already hold LN(H): up-projection + ReLU², down-projection + residual (+ the next LayerNorm).
+        LayerNorm-prologue plan: the up-projection normalises H rows with `ln_in` itself."""
         d, L = self.W.d, self.L
         M = hi - lo
-        ops.append(L.linear(xn[lo:hi], f["w1"], M, 4 * d, d, bias=f["b1"], act=gd.ACT_RELU2, out_bf16=hid[lo:hi]))
+        if self.ln_prologue:
+            ops.append(L.linear_ln(H[lo:hi], ln_in, f["w1"], M, 4 * d, d, f["b1"], act=gd.ACT_RELU2, out_bf16=hid[lo:hi]))
+            next_ln = None
+        else:
+            ops.append(L.linear(xn[lo:hi], f["w1"], M, 4 * d, d, bias=f["b1"], act=gd.ACT_RELU2, out_bf16=hid[lo:hi]))
         self._resid(ops, hid[lo:hi], f["w2"], f["b2"], M, 4 * d, H[lo:hi], next_ln, xn[lo:hi])
 
     def _build_plan(self, cond):
@@ -410,25 +438,30 @@ class SamplingChain:
             ops.append(L.linear(self.xa, W.embx_w, Mx, d, _POSE_PAD, bias=W.embx_b, rowbias=W.pe, period=T, offset=0,
                                 out_f32=X, k_alg=self.C))
             tag(len(ops) - 1, region, 0)
-            # Every LayerNorm except the first of each stream is produced by the residual GEMM in front of it.
-            ops.append(L.layernorm(X, W.layers[0]["ln_sa"], xn[:Mx], Mx, d))
-            tag(len(ops) - 1, region, 0)
-            ops.append(L.layernorm(Mem, W.layers[0]["ln_sam"], xn[Mx:], Mm, d))
-            tag(len(ops) - 1, region, 1)
+            # Default plan: every LayerNorm is a launch right behind the residual GEMM that completes its input (the first one
+            # of each stream here).  LayerNorm-prologue plan: the consuming GEMM normalises H itself (`ln_in`).
+            if not self.ln_prologue:
+                ops.append(L.layernorm(X, W.layers[0]["ln_sa"], xn[:Mx], Mx, d))
+                tag(len(ops) - 1, region, 0)
+                ops.append(L.layernorm(Mem, W.layers[0]["ln_sam"], xn[Mx:], Mm, d))
+                tag(len(ops) - 1, region, 1)
             for li, ly in enumerate(W.layers):
                 last = li == W.n_layers - 1
                 nxt = None if last else W.layers[li + 1]
                 s0 = len(ops)
-                self._attn_block(ops, ly["sa"], 0, Mx, [(0, T)], xn, qkv, ao, H, heads, next_ln=ly["ln_ca"])
+                self._attn_block(ops, ly["sa"], 0, Mx, [(0, T)], xn, qkv, ao, H, heads, next_ln=ly["ln_ca"], ln_in=ly["ln_sa"])
                 tag(s0, region, 0)
                 s0 = len(ops)
-                self._attn_block(ops, ly["sam"], Mx, R, [(Mx, Tm)], xn, qkv, ao, H, heads, next_ln=ly["ln_ca"])
+                self._attn_block(ops, ly["sam"], Mx, R, [(Mx, Tm)], xn, qkv, ao, H, heads, next_ln=ly["ln_ca"], ln_in=ly["ln_sam"])
                 tag(s0, region, 1)
                 region += 1
                 # joint attention over [x ; memory] (nn.py:105-113); last layer only the pose rows are read afterwards
                 a = ly["ca"]
                 okw = "out_f32" if self.f32act else "out_bf16"
-                ops.append(L.linear(xn, a["wqkv"], R, 3 * d, d, bias=a["bqkv"], **{okw: qkv}))
+                if self.ln_prologue:
+                    ops.append(L.linear_ln(H, ly["ln_ca"], a["wqkv"], R, 3 * d, d, a["bqkv"], out_bf16=qkv))
+                else:
+                    ops.append(L.linear(xn, a["wqkv"], R, 3 * d, d, bias=a["bqkv"], **{okw: qkv}))
                 segs = [(0, T), (Mx, Tm)]
                 qs = [(qkv[lo:, 0:], r) for lo, r in segs]
                 if last:
@@ -441,14 +474,14 @@ class SamplingChain:
                 vs = [(qkv[lo:, 2 * d:], r) for lo, r in segs]
                 ops.append(L.attention(N, heads, d // heads, qs, ks, vs, os_, a["taps"], self.f32act))
                 Ro = Mx if last else R
-                self._resid(ops, ao[:Ro], a["wo"], a["bo"], Ro, d, H[:Ro], ly["ln_ff"], xn[:Ro],
+                self._resid(ops, ao[:Ro], a["wo"], a["bo"], Ro, d, H[:Ro], None if self.ln_prologue else ly["ln_ff"], xn[:Ro],
                             ln2=ly.get("ln_ffm"), split=Mx)
                 s0 = len(ops)
-                self._ffn_block(ops, ly["ff"], 0, Mx, xn, hid, H, next_ln=(W.out_ln if last else nxt["ln_sa"]))
+                self._ffn_block(ops, ly["ff"], 0, Mx, xn, hid, H, next_ln=(W.out_ln if last else nxt["ln_sa"]), ln_in=ly["ln_ff"])
                 if "ffm" in ly:
                     tag(s0, region, 0)
                     s0 = len(ops)
-                    self._ffn_block(ops, ly["ffm"], Mx, R, xn, hid, H, next_ln=(None if last else nxt["ln_sam"]))
+                    self._ffn_block(ops, ly["ffm"], Mx, R, xn, hid, H, next_ln=(None if last else nxt["ln_sam"]), ln_in=ly["ln_ffm"])
                     tag(s0, region, 1)
         else:
             X = th.empty(Mx, d, device=dev)
@@ -470,18 +503,25 @@ class SamplingChain:
             ops.append(L.linear(self.xa, W.embx_w, Mx, d, _POSE_PAD, bias=W.embx_b, rowbias=W.pe, period=T, offset=0,
                                 out_f32=X, k_alg=self.C))
             okw = "out_f32" if self.f32act else "out_bf16"
-            ops.append(L.layernorm(X, W.layers[0]["ln_sa"], xn, Mx, d))
+            if not self.ln_prologue:
+                ops.append(L.layernorm(X, W.layers[0]["ln_sa"], xn, Mx, d))
             for li, ly in enumerate(W.layers):
                 last = li == W.n_layers - 1
-                self._attn_block(ops, ly["sa"], 0, Mx, [(0, T)], xn, qkv, ao, H, heads, next_ln=ly["ln_ca"])
+                self._attn_block(ops, ly["sa"], 0, Mx, [(0, T)], xn, qkv, ao, H, heads, next_ln=ly["ln_ca"], ln_in=ly["ln_sa"])
                 # cross attention: queries from the pose rows, K|V hoisted per chain (memory is never updated, nn.py:160-162)
                 a = ly["ca"]
-                ops.append(L.linear(xn, a["wqkv"][:d], Mx, d, d, bias=a["bqkv"][:d], **{okw: qkv[:, :d]}))
+                if self.ln_prologue:
+                    ops.append(L.linear_ln(X, ly["ln_ca"], a["wqkv"][:d], Mx, d, d, a["bqkv"][:d], out_bf16=qkv[:, :d]))
+                else:
+                    ops.append(L.linear(xn, a["wqkv"][:d], Mx, d, d, bias=a["bqkv"][:d], **{okw: qkv[:, :d]}))
                 kcol = li * 2 * d
                 ops.append(L.attention(N, heads, d // heads, [(qkv[:, 0:], T)], [(kv[:, kcol:], Tm)], [(kv[:, kcol + d:], Tm)],
                                        [(ao, T)], a["taps"], self.f32act))
-                self._resid(ops, ao, a["wo"], a["bo"], Mx, d, X, ly["ln_ff"], xn)
-                self._ffn_block(ops, ly["ff"], 0, Mx, xn, hid, H, next_ln=(W.out_ln if last else W.layers[li + 1]["ln_sa"]))
+                self._resid(ops, ao, a["wo"], a["bo"], Mx, d, X, None if self.ln_prologue else ly["ln_ff"], xn)
+                self._ffn_block(ops, ly["ff"], 0, Mx, xn, hid, H, next_ln=(W.out_ln if last else W.layers[li + 1]["ln_sa"]),
+                                ln_in=ly["ln_ff"])
+        if self.ln_prologue:  # the one LayerNorm left: out_layers.0 in front of the fused projection + DDPM update
+            ops.append(L.layernorm(H[:Mx], W.out_ln, xn[:Mx], Mx, d))
         # xn[:Mx] holds out_layers.0 LayerNorm(x) (written by the last down-projection)
         dd = gd.LinearDesc()
         dd.A, dd.W, dd.M, dd.N, dd.K, dd.lda, dd.ldw, dd.bias = _p(xn), _p(W.out_w), Mx, _POSE_PAD, d, d, d, _p(W.out_b)
@@ -587,6 +627,7 @@ class SamplingChain:
         self.x.copy_(x.to(self.device).float())
         self._pack_pose_rows()
         self.step.fill_(int(i))
+        self._pos = self.n_steps - 1 - int(i)
 
     def _pack_pose_rows(self):
         gd.check(self.L.lib.gd_pack_pose_rows_add(_p(self.x), _p(self.xa_add), _p(self.xa), self.N, self.C, self.T, _POSE_PAD,
@@ -641,6 +682,7 @@ class SamplingChain:
     def run(self, progress=False, n_steps=None):
         """Run the remaining chain (or `n_steps` steps). Returns the last step's dict."""
         total = self.n_steps if n_steps is None else n_steps
+        self.aux_step.fill_(max(self.n_steps - self._pos - total, 0))  # only the last step of this run hands back its dict
         if self.use_graph:
             self._ensure_graph()
             done = 0
@@ -653,6 +695,7 @@ class SamplingChain:
             for _ in range(total):
                 self.step_eager()
         self._pos += total
+        self.aux_step.fill_(-1)
         return self._result(max(self.n_steps - self._pos, 0))
 
     def iterate(self, progress=False):
@@ -664,6 +707,8 @@ class SamplingChain:
 
 
 _CHAINS = {}
+# LayerNorm-prologue plan as the default of new chains (set after the A/B measurement on B200)
+LN_PROLOGUE_DEFAULT = False
 
 
 def release_chains(model=None):
@@ -685,7 +730,7 @@ def chain_for(model, diffusion, shape, alg, device, **kw):
         device = th.device("cuda", th.cuda.current_device())
     opts = dict(precision=getattr(model, "precision", "bf16"), graph_steps=getattr(model, "graph_steps", 0),
                 use_graph=getattr(model, "use_graph", True), fuse_ln=getattr(model, "fuse_layernorm", False),
-                speech_impl=getattr(model, "speech_impl", "native"))
+                speech_impl=getattr(model, "speech_impl", "native"), ln_prologue=getattr(model, "ln_prologue", LN_PROLOGUE_DEFAULT))
     opts.update(kw)
     key = (id(model), id(diffusion), shape, alg, str(device), model.weights_version, tuple(sorted(opts.items())))
     ch = _CHAINS.get(key)

@@ -249,3 +249,20 @@ def test_p_sample_dict_has_every_reference_key():
     last = diffusion.p_sample_loop(model, (N, C, T), noise=x_T, model_kwargs={"wav": wav}, denoise_fn=blend, device="cuda",
                                    noise_tape=tape)
     assert set(last) == keys and th.equal(last["sample"], steps[-1]["sample"]) and th.equal(last["mean"], steps[-1]["mean"])
+
+
+@pytest.mark.parametrize("name,N", [("beat", 3), ("tedexp", 3), ("beat", 130)])
+def test_layernorm_prologue_plan_is_bit_identical_to_default_plan(name, N):
+    """LayerNorm-prologue plan (gd_linear_ln_bf16, one stand-alone LayerNorm left per step) vs the default two-kernel plan on
+    a 20-step chain: the prologue reproduces gd_layernorm bit for bit, so the final poses must be identical."""
+    from gesture_b200.generator import Generator
+    model, diffusion, C, T, L, params = build(name, "boost", respacing="ddim20", device="cuda")
+    wav = synthetic_wav(N, L, seed=31)
+    x_T, tape = noise_tape((N, C, T), 20, seed=32)
+    outs = []
+    for flag in (False, True):
+        model.ln_prologue = flag
+        outs.append(Generator(model, diffusion).generate_sample((N, C, T), wav, noise=x_T, sample_alg="ddpm", device="cuda",
+                                                                progress=False, noise_tape=tape).clone())
+    assert th.isfinite(outs[1]).all()
+    assert th.equal(outs[0], outs[1]), f"rel-L2 {rel_l2(outs[1], outs[0]):.3e}"

@@ -374,3 +374,33 @@ def test_step_row_scatter_and_helpers(gd):
     dstb = torch.empty(50, 128, device="cuda", dtype=torch.bfloat16)
     gd.check(lib.gd_cast_rows_bf16(src.data_ptr(), 123, dstb.data_ptr(), 128, 50, 123, 128, _stream()))
     assert torch.equal(dstb[:, :123], src.bfloat16()) and (dstb[:, 123:] == 0).all()
+
+
+@pytest.mark.parametrize("M,D,N,act", [(300, 256, 768, 0), (5120, 256, 1024, 1), (40960, 256, 256, 0), (77, 512, 1536, 0),
+                                       (8704, 512, 2048, 1), (35328, 512, 1536, 0), (19000, 512, 128, 0)])
+def test_linear_with_layernorm_prologue(gd, M, D, N, act):
+    """gd_linear_ln_bf16 (LayerNorm as the prologue of an A-stationary GEMM) == gd_layernorm followed by gd_linear_bf16,
+    BIT for bit (same LayerNorm arithmetic, same bf16 operand, same K order), and close to the fp32 torch statement."""
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    H = torch.randn(M, D, device="cuda", generator=g) * 2.0 + 0.5
+    W = (torch.randn(N, D, device="cuda", generator=g) / D ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    gamma = 1.0 + 0.1 * torch.randn(D, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(D, device="cuda", generator=g)
+    lib = gd.load()
+    xn = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+    gd.check(lib.gd_layernorm(H.data_ptr(), D, gamma.data_ptr(), beta.data_ptr(), xn.data_ptr(), D, M, D, 1e-5, _stream()))
+    two = torch.full((M, N), 7.0, device="cuda", dtype=torch.bfloat16)
+    d = gd.LinearDesc()
+    d.A, d.W, d.M, d.N, d.K, d.lda, d.ldw = xn.data_ptr(), W.data_ptr(), M, N, D, D, D
+    d.bias, d.act, d.out_bf16, d.ldo_bf16 = bias.data_ptr(), act, two.data_ptr(), N
+    gd.check(lib.gd_linear_bf16(C.byref(d), _stream()))
+    one = torch.full((M, N), 9.0, device="cuda", dtype=torch.bfloat16)
+    d.A, d.out_bf16 = H.data_ptr(), one.data_ptr()
+    gd.check(lib.gd_linear_ln_bf16(C.byref(d), gamma.data_ptr(), beta.data_ptr(), 1e-5, _stream()))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(H, (D,), gamma, beta, 1e-5).bfloat16().float() @ W.float().t() + bias
+    if act == 1:
+        ref = torch.relu(ref) ** 2
+    assert (one.float() - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item())
+    assert torch.equal(one, two), f"max diff {(one.float() - two.float()).abs().max().item()}"
