@@ -296,7 +296,7 @@ def strong_scaling(args, world, rank, dev, barrier):
         barrier()
         ms = e0.elapsed_time(e1)
         # chain replay alone on this rank's slice (inputs resident)
-        chain = chain_for(model, diffusion, (hi - lo, C, T), "ddpm", dev)
+        chain = chain_for(model, diffusion, (hi - lo, C, T), "ddpm", dev, allow_split=True)  # the chain generate_sample uses
         chain.begin(x_host[lo:hi].to(dev), wav_host[lo:hi].to(dev))
         th.cuda.synchronize()
         c0, c1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
@@ -316,6 +316,7 @@ def strong_scaling(args, world, rank, dev, barrier):
                "total_clips": total, "clips_per_gpu": hi - lo, "frames": T,
                "value": total * T * n_timed / (ms / 1e3), "unit": UNIT, "ms_per_chain": ms / n_timed,
                "ms_per_denoise_step": ms_replay / n_steps, "chain_replay_ms": ms_replay, "kernels_per_denoise_step": kernels,
+               "parallel_sub_chains": getattr(chain, "parts", 1),
                "first_call_s": capture_s,
                "path": "distributed.generate_sample_sharded (pinned host wav/x_T -> shard -> chain -> all_gather -> host)",
                "h2d_bytes_per_chain": (wav_host[lo:hi].numel() + x_host[lo:hi].numel()) * 4, "d2h_bytes_per_chain": total * T * C * 4,

@@ -335,20 +335,24 @@ def ddpm_step(tabs, i, x, eps, z, blend=None):
     return mean + nz * torch.exp(0.5 * _f32(tabs["posterior_log_variance_clipped"], i)) * z, x0
 
 
-def ddim_step(tabs, i, x, eps, blend=None):
-    """ddim_sample with eta=0 — gaussian_diffusion.py:443-484."""
+def ddim_step(tabs, i, x, eps, blend=None, eta=0.0, z=None):
+    """ddim_sample — gaussian_diffusion.py:443-484 (the reference only ever runs eta = 0; `z` is the step's randn_like draw)."""
     a, b = _f32(tabs["sqrt_recip_alphas_cumprod"], i), _f32(tabs["sqrt_recipm1_alphas_cumprod"], i)
     x0 = a * x - b * eps
     if blend is not None:
         x0 = blend(x0)
     eps2 = (a * x - x0) / b
-    ab_prev = _f32(tabs["alphas_cumprod_prev"], i)
-    return x0 * torch.sqrt(ab_prev) + torch.sqrt(1 - ab_prev) * eps2, x0
+    ab, ab_prev = _f32(tabs["alphas_cumprod"], i), _f32(tabs["alphas_cumprod_prev"], i)
+    sigma = eta * torch.sqrt((1 - ab_prev) / (1 - ab)) * torch.sqrt(1 - ab / ab_prev)
+    mean_pred = x0 * torch.sqrt(ab_prev) + torch.sqrt(1 - ab_prev - sigma ** 2) * eps2
+    if eta != 0.0 and i != 0 and z is not None:
+        mean_pred = mean_pred + sigma * z
+    return mean_pred, x0
 
 
 @torch.no_grad()
 def sample_chain(sd, model_type, heads, tabs, x_T, wav, tape, alg="ddpm", steps=None, blend=None,
-                 reencode_every_step=False, record=None, offset=None):
+                 reencode_every_step=False, record=None, offset=None, eta=0.0):
     """p_sample_loop / ddim_sample_loop — gaussian_diffusion.py:368-412,486-529.
     tape[k] is the k-th randn_like draw (loop order i = n-1 .. 0); `steps` restricts to the first
     `steps` iterations (bounded CPU baseline).  reencode_every_step=True reproduces the reference as
@@ -365,7 +369,7 @@ def sample_chain(sd, model_type, heads, tabs, x_T, wav, tape, alg="ddpm", steps=
         if alg == "ddpm":
             x_next, x0 = ddpm_step(tabs, i, x, eps, tape[k] if tape is not None else torch.zeros_like(x), blend)
         else:
-            x_next, x0 = ddim_step(tabs, i, x, eps, blend)
+            x_next, x0 = ddim_step(tabs, i, x, eps, blend, eta=eta, z=tape[k] if tape is not None else None)
         if record is not None:
             record(i, x, eps, x_next)
         x = x_next

@@ -100,6 +100,12 @@ class InpaintBlend:
         else:
             self.factor = th.zeros(n_frames, device=self.seed.device)
 
+    def slice(self, lo, hi):
+        """The blend of clips [lo, hi) (SplitChain: every sub-chain owns its slice)."""
+        out = object.__new__(InpaintBlend)
+        out.seed, out.mask, out.factor = self.seed[lo:hi].contiguous().clone(), self.mask[lo:hi].contiguous().clone(), self.factor.clone()
+        return out
+
     def __call__(self, pred_x_start):  # (N, C, T) -> (N, C, T); torch form, used by the un-fused progressive API
         p = pred_x_start.transpose(1, 2)
         f, m = self.factor[None, :, None], self.mask[:, :, None]
@@ -124,11 +130,12 @@ class GaussianSpacedDiffusion(GaussianDiffusion):
         super().__init__(**kwargs)
 
     # ------------------------------------------------------------------ coefficient tables for the kernels
-    def step_tables(self, alg="ddpm"):
+    def step_tables(self, alg="ddpm", eta=0.0):
         """fp32 per-step coefficients [A, B, C1, C2, sigma] consumed by gd_ddpm_update / gd_linear_ddpm.
         float64 -> fp32 happens here exactly as in `_extract_into_tensor` (gaussian_diffusion.py:691).
-        For DDIM (eta=0, :443-484) the update x0*sqrt(abar_prev) + sqrt(1-abar_prev)*(A x - x0)/B is the same
-        affine form with C1 = sqrt(abar_prev) - sqrt(1-abar_prev)/B, C2 = sqrt(1-abar_prev)*A/B, sigma = 0."""
+        For DDIM (:443-484) the update x0*sqrt(abar_prev) + s*(A x - x0)/B + sigma*z with
+        sigma = eta*sqrt((1-abar_prev)/(1-abar))*sqrt(1-abar/abar_prev), s = sqrt(1-abar_prev-sigma^2) is the same affine
+        form with C1 = sqrt(abar_prev) - s/B, C2 = s*A/B (eta = 0, the reference's only call: sigma = 0)."""
         A = th.from_numpy(self.sqrt_recip_alphas_cumprod).float()
         B = th.from_numpy(self.sqrt_recipm1_alphas_cumprod).float()
         if alg == "ddpm":
@@ -137,21 +144,23 @@ class GaussianSpacedDiffusion(GaussianDiffusion):
             sigma = th.exp(0.5 * th.from_numpy(self.posterior_log_variance_clipped).float())
         elif alg == "ddim":
             a64, b64 = self.sqrt_recip_alphas_cumprod, self.sqrt_recipm1_alphas_cumprod
-            sp, sq = np.sqrt(self.alphas_cumprod_prev), np.sqrt(1.0 - self.alphas_cumprod_prev)
+            ab, abp = self.alphas_cumprod, self.alphas_cumprod_prev
+            sig64 = eta * np.sqrt((1.0 - abp) / (1.0 - ab)) * np.sqrt(1.0 - ab / abp)
+            sp, sq = np.sqrt(abp), np.sqrt(1.0 - abp - sig64 ** 2)
             C1 = th.from_numpy(sp - sq / b64).float()
             C2 = th.from_numpy(sq * a64 / b64).float()
-            sigma = th.zeros_like(A)
+            sigma = th.from_numpy(sig64).float()
         else:
             raise ValueError(f"Unsupported sample algorithm: {alg}")
         return A, B, C1, C2, sigma
 
     # ------------------------------------------------------------------ sampling loops (gaussian_diffusion.py:331-529)
-    def _run(self, alg, model, shape, noise, denoise_fn, model_kwargs, device, progress, noise_tape, progressive):
+    def _run(self, alg, model, shape, noise, denoise_fn, model_kwargs, device, progress, noise_tape, progressive, eta=0.0):
         from .engine import chain_for  # local import: the engine needs the CUDA library
         if device is None:
             device = next(model.parameters()).device
         assert isinstance(shape, (tuple, list))
-        chain = chain_for(model, self, tuple(shape), alg, device)
+        chain = chain_for(model, self, tuple(shape), alg, device, allow_split=not progressive, eta=float(eta))
         wav = (model_kwargs or {}).get("wav")
         if wav is None:
             raise ValueError("model_kwargs['wav'] is required")
@@ -159,7 +168,7 @@ class GaussianSpacedDiffusion(GaussianDiffusion):
             noise = th.randn(*shape, device=device)
         offset = model.input_offset(model_kwargs) if hasattr(model, "input_offset") else None
         chain.begin(noise.to(device), wav.to(device), denoise_fn=denoise_fn, noise_tape=noise_tape,
-                    need_tape=(alg == "ddpm"), input_offset=offset)
+                    need_tape=(alg == "ddpm" or eta != 0.0), input_offset=offset)
         if progressive:
             return chain.iterate(progress)
         return chain.run(progress)
@@ -176,16 +185,13 @@ class GaussianSpacedDiffusion(GaussianDiffusion):
         return self._run("ddpm", model, shape, noise, denoise_fn, model_kwargs, device, progress, noise_tape, True)
 
     def ddim_sample_loop(self, model, shape, noise=None, denoise_fn=None, model_kwargs=None, device=None,
-                         progress=False, eta=0.0):
-        if eta != 0.0:
-            raise NotImplementedError("only eta=0 DDIM is on the accelerated path (the reference never passes eta)")
-        return self._run("ddim", model, shape, noise, denoise_fn, model_kwargs, device, progress, None, False)
+                         progress=False, eta=0.0, noise_tape=None):
+        """gaussian_diffusion.py:486-529.  eta != 0 adds sigma_t * noise per step (`noise_tape` replaces the randn_like draws)."""
+        return self._run("ddim", model, shape, noise, denoise_fn, model_kwargs, device, progress, noise_tape, False, eta=eta)
 
     def ddim_sample_loop_progressive(self, model, shape, noise=None, denoise_fn=None, model_kwargs=None, device=None,
-                                     progress=False, eta=0.0):
-        if eta != 0.0:
-            raise NotImplementedError("only eta=0 DDIM is on the accelerated path")
-        return self._run("ddim", model, shape, noise, denoise_fn, model_kwargs, device, progress, None, True)
+                                     progress=False, eta=0.0, noise_tape=None):
+        return self._run("ddim", model, shape, noise, denoise_fn, model_kwargs, device, progress, noise_tape, True, eta=eta)
 
 
     # ------------------------------------------------------------------ variational bound (gaussian_diffusion.py:571-678)

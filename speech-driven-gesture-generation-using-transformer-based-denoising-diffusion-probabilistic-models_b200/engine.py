@@ -196,7 +196,7 @@ class SamplingChain:
     """One (model, diffusion, batch shape, algorithm) sampling context: buffers + plan + captured graph."""
 
     def __init__(self, model, diffusion, shape, alg, device, precision="bf16", graph_steps=1, use_graph=True,
-                 fuse_ln=False, speech_impl="native", ln_prologue=False):
+                 fuse_ln=False, speech_impl="native", ln_prologue=False, eta=0.0):
         if device.type != "cuda":
             raise gd.GdError("the DDPM sampling path runs only on a CUDA device (sm_100a); there is no CPU fallback")
         # the model is held weakly: the chain cache must not keep a dropped model (and its tape / graph) alive
@@ -216,7 +216,9 @@ class SamplingChain:
         if self.C != self.W.C:
             raise ValueError(f"shape[1]={self.C} does not match the model's d_pose={self.W.C}")
         self.n_steps = diffusion.num_timesteps
-        self.tabs = [t.to(device).contiguous() for t in diffusion.step_tables(alg)]
+        self.eta = float(eta)  # DDIM only (gaussian_diffusion.py:463-467)
+        self.tabs = [t.to(device).contiguous() for t in (diffusion.step_tables(alg, self.eta) if alg == "ddim" else
+                                                         diffusion.step_tables(alg))]
         self.step = th.zeros(1, dtype=th.int32, device=device)
         # loop index whose step writes the optional outputs (eps / x0 / mean / raw_x0); -1 = every step.  A chain replay
         # needs them for its last step only: 4 x (N,C,T) fp32 stores saved in each of the other 999 steps.
@@ -535,9 +537,10 @@ class SamplingChain:
         return ops
 
     # ------------------------------------------------------------------ public driver
-    def begin(self, x_T, wav, denoise_fn=None, noise_tape=None, need_tape=True, input_offset=None):
+    def begin(self, x_T, wav, denoise_fn=None, noise_tape=None, need_tape=True, input_offset=None, rng_consumed=False):
         """Load x_T, compute the conditioning once, (re)build the plan, reset the step counter.  `input_offset`
-        (N,C,T) is the Inpaint model's loop-invariant offset of the denoiser input (model.py:161-165)."""
+        (N,C,T) is the Inpaint model's loop-invariant offset of the denoiser input (model.py:161-165).  `rng_consumed`:
+        the caller (SplitChain) has already drawn this chain's share of the reference's per-step random numbers."""
         from .diffusion import InpaintBlend
         if denoise_fn is not None and not isinstance(denoise_fn, InpaintBlend):
             raise NotImplementedError("denoise_fn must be an InpaintBlend (the fused in-paint epilogue); "
@@ -562,7 +565,7 @@ class SamplingChain:
                     self.tape.copy_(tp)
                 else:
                     self.tape = tp
-        elif self.alg == "ddim" and getattr(self.model, "match_reference_rng", True):
+        elif self.alg == "ddim" and not rng_consumed and getattr(self.model, "match_reference_rng", True):
             # the reference's ddim_sample draws th.randn_like(x) at every step even though eta = 0 multiplies it away
             # (gaussian_diffusion.py:475): consume the same draws so that a seeded sequence of calls (generate_sequence
             # windows, repeated generate_sample) sees the same x_T stream afterwards
@@ -633,10 +636,8 @@ class SamplingChain:
         gd.check(self.L.lib.gd_pack_pose_rows_add(_p(self.x), _p(self.xa_add), _p(self.xa), self.N, self.C, self.T, _POSE_PAD,
                                                   self.L.stream()), "gd_pack_pose_rows_add")
 
-    def _ensure_graph(self):
-        if self.graph is not None or not self.use_graph:
-            return
-        # one eager step on a side stream warms every kernel (func attributes, tensor-map encode path)
+    def _warm_step(self):
+        """One eager step on a side stream warms every kernel (func attributes, tensor-map encode path); state restored."""
         saved = (self.x.clone(), self.xa.clone(), self.step.clone())
         s = th.cuda.Stream(device=self.device)
         s.wait_stream(th.cuda.current_stream())
@@ -645,6 +646,12 @@ class SamplingChain:
         th.cuda.current_stream().wait_stream(s)
         th.cuda.synchronize()
         self.x.copy_(saved[0]); self.xa.copy_(saved[1]); self.step.copy_(saved[2])
+        return saved
+
+    def _ensure_graph(self):
+        if self.graph is not None or not self.use_graph:
+            return
+        saved = self._warm_step()
         import time
         free0 = th.cuda.mem_get_info(self.device)[0]
         t0 = time.perf_counter()
@@ -706,6 +713,121 @@ class SamplingChain:
             yield {k: v.clone() for k, v in self._result(i).items()}
 
 
+class SplitChain:
+    """K independent sub-chains over contiguous clip slices, captured as PARALLEL BRANCHES of one CUDA graph.
+
+    Clips never interact, so a batch may be sampled as several smaller batches.  At small batches a
+    denoise step is bound by the serial critical path of its 49-192 kernels, not by throughput (B200, beat-ours:
+    64 clips 0.21 ms/step, 128 clips 0.30 ms/step - most SMs idle): two or four sub-chains running side by side fill the
+    idle SMs, and because every kernel is batch-invariant the poses are bit-identical to the un-split run
+    (tests/test_batch_parity_gpu.py).  Only the whole-chain entry points (`p_sample_loop` / `ddim_sample_loop`) use it; the
+    progressive / teacher-forced / bpd paths keep a single chain."""
+
+    def __init__(self, model, diffusion, shape, alg, device, parts, **opts):
+        self.N, self.C, self.T = shape
+        base, extra = divmod(self.N, parts)
+        self.bounds, lo = [], 0
+        for k in range(parts):
+            hi = lo + base + (1 if k < extra else 0)
+            self.bounds.append((lo, hi))
+            lo = hi
+        opts = dict(opts, use_graph=False)  # the children never capture on their own
+        self.children = [SamplingChain(model, diffusion, (hi - lo, self.C, self.T), alg, device, **opts) for lo, hi in self.bounds]
+        self.streams = [th.cuda.Stream(device=device) for _ in self.children]
+        self.device, self.alg, self.diffusion = device, alg, diffusion
+        self.n_steps = diffusion.num_timesteps
+        self.speech_impl = self.children[0].speech_impl
+        self.graph, self.graph_info, self._keys = None, {}, None
+        self.parts = parts
+
+    @property
+    def plan(self):  # all launches of one denoise step (bench.py counts FLOPs / kernels from it)
+        return [op for ch in self.children for op in ch.plan]
+
+    def begin(self, x_T, wav, denoise_fn=None, noise_tape=None, need_tape=True, input_offset=None):
+        dev, n = self.device, self.n_steps
+        if need_tape and noise_tape is None:
+            # the same draws, in the same order, as the single chain (one (N,C,T) normal_() per step, loop order)
+            noise_tape = th.empty(n, self.N, self.C, self.T, device=dev)
+            for k in range(n):
+                noise_tape[k].normal_()
+        elif self.alg == "ddim" and getattr(self.children[0].model, "match_reference_rng", True):
+            scratch = th.empty(self.N, self.C, self.T, device=dev)
+            for _ in range(n):
+                scratch.normal_()
+        for ch, (lo, hi) in zip(self.children, self.bounds):  # the draws above were made once for the whole batch
+            ch.begin(x_T[lo:hi], wav[lo:hi], denoise_fn=None if denoise_fn is None else denoise_fn.slice(lo, hi),
+                     noise_tape=None if noise_tape is None else noise_tape[:, lo:hi], need_tape=need_tape,
+                     input_offset=None if input_offset is None else input_offset[lo:hi], rng_consumed=True)
+        keys = tuple(ch._plan_key for ch in self.children)
+        if keys != self._keys:
+            self._keys, self.graph = keys, None
+
+    def _capture(self):
+        import time
+        saved = [ch._warm_step() for ch in self.children]
+        free0 = th.cuda.mem_get_info(self.device)[0]
+        t0 = time.perf_counter()
+        g = th.cuda.CUDAGraph()
+        with th.cuda.graph(g):
+            main = th.cuda.current_stream()
+            for ch, s in zip(self.children, self.streams):
+                s.wait_stream(main)
+                with th.cuda.stream(s):
+                    for _ in range(self.n_steps):
+                        ch.step_eager()
+            for s in self.streams:
+                main.wait_stream(s)
+        th.cuda.synchronize()
+        t1 = time.perf_counter()
+        self.graph = g
+
+        def restore():
+            for ch, sv in zip(self.children, saved):
+                ch.x.copy_(sv[0]); ch.xa.copy_(sv[1]); ch.step.copy_(sv[2])
+        restore()
+        g.replay()
+        th.cuda.synchronize()
+        restore()
+        self.graph_info = {"steps_per_graph": self.n_steps, "parallel_sub_chains": self.parts,
+                           "kernel_nodes": self.n_steps * len(self.plan), "capture_s": round(t1 - t0, 3),
+                           "first_replay_s": round(time.perf_counter() - t1, 3),
+                           "device_bytes": int(max(free0 - th.cuda.mem_get_info(self.device)[0], 0))}
+
+    def run(self, progress=False, n_steps=None):
+        if n_steps is not None and n_steps != self.n_steps:
+            raise ValueError("a split chain runs whole chains only")
+        if self.graph is None:
+            self._capture()
+        for ch in self.children:
+            ch.aux_step.fill_(0)  # only the last step hands back its dict
+        self.graph.replay()
+        outs = []
+        for ch in self.children:
+            ch._pos = self.n_steps
+            ch.aux_step.fill_(-1)
+            outs.append(ch._result(0))
+        return {k: th.cat([o[k] for o in outs], dim=0) for k in outs[0]}
+
+
+def sub_chain_count(model, shape, alg):
+    """How many parallel sub-chains a whole-chain sampling call is split into (1 = none).  `model.sub_chains` / GD_SUBCHAINS:
+    an int, or "auto" (default): split while a sub-batch keeps at least AUTO_MIN_ROWS token rows and the batch is small
+    enough that one chain leaves SMs idle (measured on B200)."""
+    want = os.environ.get("GD_SUBCHAINS", getattr(model, "sub_chains", "auto"))
+    N, _, T = shape
+    if str(want) != "auto":
+        return max(1, min(int(want), N))
+    rows = N * T
+    parts = 1
+    while parts < AUTO_MAX_PARTS and rows // (2 * parts) >= AUTO_MIN_ROWS and rows <= AUTO_SPLIT_BELOW_ROWS:
+        parts *= 2
+    return parts
+
+
+AUTO_MIN_ROWS, AUTO_SPLIT_BELOW_ROWS, AUTO_MAX_PARTS = 1 << 30, 0, 4  # auto splitting off until measured (set below)
+
+
 _CHAINS = {}
 # LayerNorm-prologue plan as the default of new chains (set after the A/B measurement on B200, see DESIGN.md)
 LN_PROLOGUE_DEFAULT = False
@@ -721,7 +843,7 @@ def release_chains(model=None):
         th.cuda.empty_cache()
 
 
-def chain_for(model, diffusion, shape, alg, device, **kw):
+def chain_for(model, diffusion, shape, alg, device, allow_split=False, **kw):
     """Cache of sampling contexts keyed by (model, diffusion, shape, algorithm): buffers and graphs are reused.  Entries of
     a model are dropped when the model is garbage-collected, when its weights change (load_state_dict / .to()) and when
     another batch shape is requested, so the cache holds at most one batch shape per live model."""
@@ -730,14 +852,17 @@ def chain_for(model, diffusion, shape, alg, device, **kw):
         device = th.device("cuda", th.cuda.current_device())
     opts = dict(precision=getattr(model, "precision", "bf16"), graph_steps=getattr(model, "graph_steps", 0),
                 use_graph=getattr(model, "use_graph", True), fuse_ln=getattr(model, "fuse_layernorm", False),
-                speech_impl=getattr(model, "speech_impl", "native"), ln_prologue=getattr(model, "ln_prologue", LN_PROLOGUE_DEFAULT))
+                speech_impl=getattr(model, "speech_impl", "native"), ln_prologue=getattr(model, "ln_prologue", LN_PROLOGUE_DEFAULT),
+                eta=0.0)
     opts.update(kw)
-    key = (id(model), id(diffusion), shape, alg, str(device), model.weights_version, tuple(sorted(opts.items())))
+    parts = sub_chain_count(model, shape, alg) if (allow_split and opts["use_graph"] and not opts["graph_steps"]) else 1
+    key = (id(model), id(diffusion), shape, alg, str(device), model.weights_version, tuple(sorted(opts.items())), parts)
     ch = _CHAINS.get(key)
     if ch is None:
         for k in [k for k in _CHAINS if k[0] == id(model) and (k[2] != shape or k[5] != model.weights_version)]:
             del _CHAINS[k]  # keep one batch shape per model resident; chains of superseded weights are dead
-        ch = SamplingChain(model, diffusion, shape, alg, device, **opts)
+        ch = (SamplingChain(model, diffusion, shape, alg, device, **opts) if parts <= 1 else
+              SplitChain(model, diffusion, shape, alg, device, parts, **opts))
         _CHAINS[key] = ch
         if not getattr(model, "_gd_chain_finalizer", False):
             weakref.finalize(model, release_chains_by_id, id(model))

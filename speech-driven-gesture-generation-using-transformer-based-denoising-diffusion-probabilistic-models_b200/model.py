@@ -106,7 +106,15 @@ class Speech2GestureDenoiser(nn.Module):
             raise GdError("the denoiser runs only on a CUDA device (sm_100a kernels); there is no CPU fallback")
         t0 = int(t.reshape(-1)[0].item())
         if not bool((t == t0).all()):
-            raise NotImplementedError("per-clip timesteps are not supported: the sampling loops use one t per step")
+            # per-clip timesteps (models/model.py:12-15: `t` is (N,); training and calc_bpd's callers pass mixed values):
+            # clips sharing a timestep go through the kernels together; the kernels are batch-invariant, so every clip's
+            # eps is what a uniform-t call would give it
+            out = th.empty_like(x_t, dtype=th.float32)
+            for tv in th.unique(t).tolist():
+                idx = (t == tv).nonzero(as_tuple=True)[0]
+                kw = {k: (v[idx] if k == "wav" else v[:, idx]) for k, v in model_kwargs.items()}  # inpaint_* are (T,N,.)
+                out[idx] = self.forward(x_t[idx].contiguous(), t[idx], **kw)
+            return out
         i = self._diffusion.timestep_map.index(t0)
         chain = chain_for(self, self._diffusion, tuple(x_t.shape), "ddpm", x_t.device, use_graph=False)
         chain.begin(x_t, model_kwargs["wav"].to(x_t.device), need_tape=False, input_offset=self.input_offset(model_kwargs))

@@ -246,6 +246,38 @@ def bpd():
     print("bpd written", {k: v.shape for k, v in out.items()}, out["total_bpd"])
 
 
+def extras():
+    """Round-2 boundary cases, beat-ours, boosted weights, through the reference's own entry points:
+      * DDIM with eta = 0.5 (ddim_sample_loop, gaussian_diffusion.py:443-484,486-529): 50-step respaced process, fixed tape;
+      * one denoiser call with a DIFFERENT timestep per clip (models/model.py:12-15; what training and calc_bpd pass)."""
+    mp, d_pose, T, L = ref_params("beat", "ddim50")
+    th.manual_seed(0)
+    model, diffusion, *_ = create_model(d_pose=d_pose, model_params=mp, is_training=False)
+    model.eval()
+    model.load_state_dict(boosted_state_dict(model.state_dict(), seed=1))
+    n = 3
+    shape = (n, d_pose, T)
+    wav = synthetic_wav(n, L, seed=71)
+    x_T, tape = noise_tape(shape, 50, seed=72)
+    out = {}
+    it = iter(tape)
+    real = th.randn_like
+    th.randn_like = lambda x: next(it)
+    try:
+        with th.no_grad():
+            res = diffusion.ddim_sample_loop(model, shape, noise=x_T, model_kwargs={"wav": wav}, device="cpu", eta=0.5)
+    finally:
+        th.randn_like = real
+    out["ddim50_eta05.final"] = res["sample"].numpy()
+    t = th.tensor([diffusion.timestep_map[k] for k in (49, 7, 0)], dtype=th.long)  # original timesteps, one per clip
+    x = th.randn(shape, generator=th.Generator().manual_seed(73))
+    with th.no_grad():
+        out["eps_per_clip_t"] = model(x, t, wav=wav).numpy()
+    out["per_clip_t"] = t.numpy()
+    np.savez_compressed(os.path.join(HERE, "beat_extras_golden.npz"), **out)
+    print("extras written", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     th.set_num_threads(8)
@@ -261,3 +293,5 @@ if __name__ == "__main__":
         bpd()
     if what in ("inpaint", "all"):
         inpaint()
+    if what in ("extras", "all"):
+        extras()

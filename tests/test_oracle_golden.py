@@ -209,3 +209,23 @@ def test_oracle_inpaint_model_variant():
     out = orc.sample_chain(sd, "inpaint", heads, tabs, x_T, wav, tape, alg="ddpm", offset=off,
                            blend=lambda x0: orc.inpaint_blend(x0, seed_poses, masks, f))
     assert rel_l2(out.transpose(1, 2), g["ddpm20_inpaint.final"]) < 1e-3
+
+
+def test_oracle_ddim_eta_and_per_clip_t_vs_reference():
+    """Round-2 boundary cases against tests/golden/beat_extras_golden.npz (written by the unmodified reference): DDIM with
+    eta = 0.5 over a 50-step process, and one denoiser call with a different timestep per clip."""
+    import numpy as np
+    from oracle import ddpm_oracle as orc
+    from util import GOLDEN, build, noise_tape, rel_l2, synthetic_wav
+    g = np.load(f"{GOLDEN}/beat_extras_golden.npz")
+    model, diffusion, C, T, L, params = build("beat", "boost", respacing="ddim50")
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    tabs = orc.spaced_diffusion_tables("linear", 1000, "ddim50")
+    wav = synthetic_wav(3, L, seed=71)
+    x_T, tape = noise_tape((3, C, T), 50, seed=72)
+    out = orc.sample_chain(sd, params.type, params.Decoder.heads, tabs, x_T, wav, tape, alg="ddim", eta=0.5)
+    assert rel_l2(out, g["ddim50_eta05.final"]) < 1e-3
+    x = th.randn(3, C, T, generator=th.Generator().manual_seed(73))
+    with th.no_grad():
+        eps = orc.denoiser(sd, params.type, params.Decoder.heads, x, th.from_numpy(g["per_clip_t"]), orc.speech_features(sd, wav))
+    assert rel_l2(eps, g["eps_per_clip_t"]) < 1e-4
