@@ -76,6 +76,8 @@ typedef struct gd_linear_desc {
     int32_t ldo_f32;
     void* out_bf16;
     int32_t ldo_bf16;
+    int32_t max_ctas;   /* ABI 4: > 0 caps the persistent grid (SMs this launch may occupy) so that kernels of two concurrent
+                           streams share the GPU by SM count instead of queueing behind each other; 0 = every SM */
 } gd_linear_desc;
 
 int gd_linear_bf16(const gd_linear_desc* d, void* stream);
@@ -210,6 +212,7 @@ typedef struct gd_attn_desc {
      * (models/nn.py:105-113, transformer.py:19-44), so q[1] = memory row 0 of every clip, q_rows[1] = 1,
      * q_clip_stride[1] = memory rows per clip, out[1] = NULL. */
     int32_t q_clip_stride[2];
+    int32_t max_ctas_sms; /* ABI 4: > 0 sizes the persistent grid for that many SMs (see gd_linear_desc.max_ctas); 0 = all */
 } gd_attn_desc;
 
 int gd_dconv_attention(const gd_attn_desc* d, void* stream);

@@ -17,7 +17,7 @@ class LinearDesc(C.Structure):
     _fields_ = [("A", c_vp), ("W", c_vp), ("M", c_i32), ("N", c_i32), ("K", c_i32), ("lda", c_i32), ("ldw", c_i32),
                 ("bias", c_vp), ("rowbias", c_vp), ("rowbias_period", c_i32), ("rowbias_offset", c_i32),
                 ("residual", c_vp), ("ldr", c_i32), ("act", c_i32), ("out_f32", c_vp), ("ldo_f32", c_i32),
-                ("out_bf16", c_vp), ("ldo_bf16", c_i32)]
+                ("out_bf16", c_vp), ("ldo_bf16", c_i32), ("max_ctas", c_i32)]
 
 
 class DdpmDesc(C.Structure):
@@ -38,7 +38,7 @@ class AttnDesc(C.Structure):
                 ("kv_rows", c_i32 * 2), ("kv_ld", c_i32 * 2), ("out", c_vp * 2), ("out_ld", c_i32 * 2),
                 ("conv_wq", c_vp), ("conv_bq", c_vp), ("conv_wk", c_vp), ("conv_bk", c_vp), ("conv_wv", c_vp),
                 ("conv_bv", c_vp), ("n_clips", c_i32), ("heads", c_i32), ("d_k", c_i32), ("scale", c_f32),
-                ("q_clip_stride", c_i32 * 2)]
+                ("q_clip_stride", c_i32 * 2), ("max_ctas_sms", c_i32)]
 
 
 class ConvDesc(C.Structure):

@@ -650,7 +650,7 @@ static int launch_attention_tma(const AttnParams& p, int n_clips, cudaStream_t s
     int per_sm = 0;
     GD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
     if (per_sm < 1) return set_error(GD_ERR_CUDA, "gd_dconv_attention: kernel does not fit on an SM (smem %zu B)", smem);
-    int grid = per_sm * sm_count();
+    int grid = per_sm * ((p.max_sms > 0 && p.max_sms < sm_count()) ? p.max_sms : sm_count());
     if (grid > geo.n_items) grid = geo.n_items;
     GD_CUDA_CHECK(launch_k(kern, grid, warps * 32, smem, s, 1, tq[0], tq[1], tk[0], tk[1], tv[0], tv[1], p, geo));
     count_launch();
@@ -709,6 +709,7 @@ static int run_attention(const gd_attn_desc* d, bool fp32_in, void* stream) {
     }
     p.wq = d->conv_wq, p.bq = d->conv_bq, p.wk = d->conv_wk, p.bk = d->conv_bk, p.wv = d->conv_wv, p.bv = d->conv_bv;
     p.heads = d->heads;
+    p.max_sms = d->max_ctas_sms;
     p.scale_log2 = d->scale * 1.4426950408889634f;
     p.Lq = p.q_rows[0] + p.q_rows[1];
     p.Lk = p.kv_rows[0] + p.kv_rows[1];

@@ -16,6 +16,7 @@ struct AttnParams {
     int q_stride[2];  // rows between consecutive clips of a query segment (== q_rows unless the segment is a halo view)
     const float *wq, *bq, *wk, *bk, *wv, *bv;
     int heads, Lq, Lk;
+    int max_sms;  // host only: SMs the persistent grid is sized for (0 = all)
     float scale_log2;  // d_k^-1/2 * log2(e)
 };
 

@@ -49,6 +49,7 @@ struct GemmParams {
     __nv_bfloat16* out_bf16;
     int ldo_bf16;
     int reduce_add;  // MODE_TMA_F32: 1 = out += result (in-place residual), 0 = out = result
+    int max_ctas;    // host only: cap of the persistent grid (0 = every SM)
     gd_ddpm_desc ddpm;
     // MODE_CONV: k-block kb reads A rows m0 + tap_shift[kb / kb_per_tap], columns ((kb % kb_per_tap) * 64) mod a_cols
     int kb_per_tap, a_cols;
@@ -695,7 +696,8 @@ static int launch_gemm_cl(const GemmParams& p, const void* A, int lda, const voi
     }
     const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
     const int work = ((m_tiles + CL - 1) / CL) * (p.N / BN);  // cluster-level work items
-    const int max_clusters = sm_count() / CL;
+    const int sms = (p.max_ctas > 0 && p.max_ctas < sm_count()) ? p.max_ctas : sm_count();
+    const int max_clusters = sms / CL > 0 ? sms / CL : 1;
     const int grid = (work < max_clusters ? work : max_clusters) * CL;
     GD_CUDA_CHECK(launch_k(gemm_bf16_tn_kernel<BN, MODE, CL>, grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream, CL, ta, tb, tout, p));
     count_launch();
@@ -780,6 +782,7 @@ extern "C" int gd_linear_bf16(const gd_linear_desc* d, void* stream) {
     p.residual = d->residual, p.ldr = d->ldr, p.act = d->act;
     p.out_f32 = d->out_f32, p.ldo_f32 = d->ldo_f32;
     p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(d->out_bf16), p.ldo_bf16 = d->ldo_bf16;
+    p.max_ctas = d->max_ctas;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const int m_tiles = (d->M + BLOCK_M - 1) / BLOCK_M;
     // epilogue flavour: TMA stores for the two hot shapes, the per-row path for everything else

@@ -122,6 +122,7 @@ class _Launcher:
     def __init__(self):
         self.lib = gd.load()
         self.keep = []  # tensors that descriptors point into
+        self.sm_cap = 0  # > 0: persistent kernels created now are sized for that many SMs (concurrent-lane partitioning)
 
     @staticmethod
     def stream():
@@ -137,6 +138,7 @@ class _Launcher:
         d.act = act
         d.out_f32, d.ldo_f32 = _p(out_f32), (ldo32 or (out_f32.stride(0) if out_f32 is not None else 0))
         d.out_bf16, d.ldo_bf16 = _p(out_bf16), (ldo16 or (out_bf16.stride(0) if out_bf16 is not None else 0))
+        d.max_ctas = self.sm_cap
         lib = self.lib
         nbytes = 2 * M * K + 2 * N * K + (4 * M * N if residual is not None else 0) + \
             (4 * M * N if out_f32 is not None else 0) + (2 * M * N if out_bf16 is not None else 0)
@@ -185,6 +187,7 @@ class _Launcher:
             a.out[s], a.out_ld[s] = _p(t), t.stride(0)
         a.conv_wq, a.conv_bq, a.conv_wk, a.conv_bk, a.conv_wv, a.conv_bv = [_p(t) for t in taps]
         a.n_clips, a.heads, a.d_k, a.scale = n_clips, heads, d_k, 1.0 / math.sqrt(d_k)
+        a.max_ctas_sms = self.sm_cap
         fn = self.lib.gd_dconv_attention_f32in if f32in else self.lib.gd_dconv_attention
         Lq, Lk, dm, es = sum(seg[1] for seg in q[:len(out)]), sum(r for _, r in k), heads * d_k, (4 if f32in else 2)
         flops = n_clips * (4 * Lq * Lk * dm + 6 * dm * (Lq + 2 * Lk))  # QK^T + PV + three 3-tap convs
@@ -433,12 +436,22 @@ class SamplingChain:
                 for op in ops[start:]:
                     op.group, op.lane = group, lane
             region = 1
+            # SM partitioning of the concurrent regions (GD_SM_PARTITION / model.sm_partition): the persistent kernels of the
+            # pose lane are sized for Mx/R of the SMs and those of the memory lane for the rest, so the two lanes run side by
+            # side instead of queueing behind each other's 148-CTA grids
+            part = bool(int(os.environ.get("GD_SM_PARTITION", int(getattr(self.model, "sm_partition", SM_PARTITION_DEFAULT))))) \
+                and self.concurrent
+            n_sm = th.cuda.get_device_properties(dev).multi_processor_count
+            cap0 = max(8, int(round(n_sm * Mx / R))) if part else 0
+            cap1 = (n_sm - cap0) if part else 0
             a_sc = (_p(Mem), _p(cond["mem_init"]), _p(cond["mem_tab"]), _p(self.step), N, Tm, 0, d, d)
             ops.append(Op(lambda: gd.check(lib.gd_scatter_step_row_f32(*a_sc, L.stream()), "gd_scatter_step_row_f32"),
                           "scatter", 0, 8 * Mm * d))
             tag(len(ops) - 1, region, 1)
+            L.sm_cap = cap0
             ops.append(L.linear(self.xa, W.embx_w, Mx, d, _POSE_PAD, bias=W.embx_b, rowbias=W.pe, period=T, offset=0,
                                 out_f32=X, k_alg=self.C))
+            L.sm_cap = 0
             tag(len(ops) - 1, region, 0)
             # Default plan: every LayerNorm is a launch right behind the residual GEMM that completes its input (the first one
             # of each stream here).  LayerNorm-prologue plan: the consuming GEMM normalises H itself (`ln_in`).
@@ -451,11 +464,14 @@ class SamplingChain:
                 last = li == W.n_layers - 1
                 nxt = None if last else W.layers[li + 1]
                 s0 = len(ops)
+                L.sm_cap = cap0
                 self._attn_block(ops, ly["sa"], 0, Mx, [(0, T)], xn, qkv, ao, H, heads, next_ln=ly["ln_ca"], ln_in=ly["ln_sa"])
                 tag(s0, region, 0)
                 s0 = len(ops)
+                L.sm_cap = cap1
                 self._attn_block(ops, ly["sam"], Mx, R, [(Mx, Tm)], xn, qkv, ao, H, heads, next_ln=ly["ln_ca"], ln_in=ly["ln_sam"])
                 tag(s0, region, 1)
+                L.sm_cap = 0
                 region += 1
                 # joint attention over [x ; memory] (nn.py:105-113); last layer only the pose rows are read afterwards
                 a = ly["ca"]
@@ -479,12 +495,15 @@ class SamplingChain:
                 self._resid(ops, ao[:Ro], a["wo"], a["bo"], Ro, d, H[:Ro], None if self.ln_prologue else ly["ln_ff"], xn[:Ro],
                             ln2=ly.get("ln_ffm"), split=Mx)
                 s0 = len(ops)
+                L.sm_cap = cap0 if "ffm" in ly else 0
                 self._ffn_block(ops, ly["ff"], 0, Mx, xn, hid, H, next_ln=(W.out_ln if last else nxt["ln_sa"]), ln_in=ly["ln_ff"])
                 if "ffm" in ly:
                     tag(s0, region, 0)
                     s0 = len(ops)
+                    L.sm_cap = cap1
                     self._ffn_block(ops, ly["ffm"], Mx, R, xn, hid, H, next_ln=(None if last else nxt["ln_sam"]), ln_in=ly["ln_ffm"])
                     tag(s0, region, 1)
+                L.sm_cap = 0
         else:
             X = th.empty(Mx, d, device=dev)
             H = X
@@ -831,6 +850,8 @@ AUTO_MIN_ROWS, AUTO_SPLIT_BELOW_ROWS, AUTO_MAX_PARTS = 1 << 30, 0, 4  # auto spl
 _CHAINS = {}
 # LayerNorm-prologue plan as the default of new chains (set after the A/B measurement on B200)
 LN_PROLOGUE_DEFAULT = False
+# SM partitioning of the concurrent pose / memory lanes of the tedexp plan (set after the A/B measurement on B200)
+SM_PARTITION_DEFAULT = False
 
 
 def release_chains(model=None):
