@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgd_b200.so")
+# GD_LIB points at another build of the same ABI (A/B runs of compile-time variants, profiles/chain_ab.py)
+LIB_PATH = os.environ.get("GD_LIB") or os.path.join(_HERE, "libgd_b200.so")
 
 c_i32, c_f32, c_vp = C.c_int32, C.c_float, C.c_void_p
 

@@ -34,7 +34,11 @@ constexpr int MODE_CONV = 4;      // implicit-GEMM convolution over pixel rows (
 // Split-precision convolutions with operand reuse: a pipeline stage holds the tiles of one (tap, 64-channel block) and the
 // MMA issuer forms all three bf16x3 products from them, so no tile is loaded twice (-1/3 shared-memory fill):
 constexpr int MODE_CONV_S1 = 5;   // rows [hi(32) | lo(32)]: 1 A tile, B tiles [Whi|Whi] and [Wlo|0]      -> A*B0 + A*B1
-constexpr int MODE_CONV_S2 = 6;   // rows [hi(c) | lo(c)], c % 64 == 0: A tiles hi, lo; B tiles Whi, Wlo  -> hi*Whi + lo*Whi + hi*Wlo
+constexpr int MODE_CONV_S2 = 6;
+// staging bytes per epilogue warp of the fp32 (reduce-add) epilogue: 4096 = one 32x32 fp32 chunk, 8192 = a ring of two
+#ifndef GD_F32_STAGING
+#define GD_F32_STAGING 4096
+#endif   // rows [hi(c) | lo(c)], c % 64 == 0: A tiles hi, lo; B tiles Whi, Wlo  -> hi*Whi + lo*Whi + hi*Wlo
 
 struct GemmParams {
     int M, N, K;
@@ -63,14 +67,14 @@ struct GemmParams {
     int out_img_stride, out_y_stride, out_x_stride, out_offset;  // output row of a kept pixel
 };
 
-template <int BN, int CL, int NA = 1, int NB = 1>
+template <int BN, int CL, int NA = 1, int NB = 1, int STG = 4096>
 struct GemmCfg {
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
     static constexpr int B_BYTES = (BN / CL) * BLOCK_K * 2;  // a CTA of a pair stores half of the W tile
     static constexpr int STAGE_BYTES = NA * A_BYTES + NB * B_BYTES;  // NA / NB tiles per stage (MODE_CONV_S*: operand reuse)
     // per epilogue warp one 32-row x 32-column fp32 staging tile.  A deeper ring and a shared-memory copy of the bias were
     // measured and changed nothing (the epilogue is not waiting on them) while costing a pipeline stage, so: 4 KB / warp.
-    static constexpr int STAGING_PER_WARP = 4096;
+    static constexpr int STAGING_PER_WARP = STG;
     static constexpr int STAGING_BYTES = EPI_WARPS * STAGING_PER_WARP;
     static constexpr int SMEM_LIMIT = 227 * 1024;
     static constexpr int STAGES_FIT = (SMEM_LIMIT - 2048 - STAGING_BYTES) / STAGE_BYTES;
@@ -287,7 +291,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
     constexpr bool IS_CONV = MODE >= MODE_CONV;
     constexpr int NA = (MODE == MODE_CONV_S2) ? 2 : 1, NB = (MODE >= MODE_CONV_S1) ? 2 : 1;
-    using Cfg = GemmCfg<BN, CL, NA, NB>;
+    using Cfg = GemmCfg<BN, CL, NA, NB, (MODE == MODE_TMA_F32) ? GD_F32_STAGING : 4096>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -673,7 +677,7 @@ static int make_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t rows, ui
 
 template <int BN, int MODE, int CL>
 static int launch_gemm_cl(const GemmParams& p, const void* A, int lda, const void* W, int ldw, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN, CL>;
+    using Cfg = GemmCfg<BN, CL, 1, 1, (MODE == MODE_TMA_F32) ? GD_F32_STAGING : 4096>;
     CUtensorMap ta, tb, tout;
     int rc = make_tmap_2d_bf16(&ta, A, p.M, p.K, lda, BLOCK_M);
     if (rc) return rc;

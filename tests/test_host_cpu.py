@@ -136,3 +136,47 @@ def test_bench_reference_arm_prints_one_json_line():
     # the unmodified reference when oracle/_ref is staged (oracle/make_ref.py), else the oracle port
     assert d["cpu_baseline"]["kind"] == ("reference" if ref_runner.available() else "port")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["cores"] >= 1
+
+
+def test_ddim_eta_tables_reduce_to_the_deterministic_sampler():
+    """step_tables('ddim', eta): eta = 0 gives sigma = 0 and the round-1 coefficients; eta = 1 with every step kept makes the
+    DDIM variance the ancestral posterior variance (gaussian_diffusion.py:463-467 vs :120-124)."""
+    import numpy as np
+    from gesture_b200.diffusion import GaussianSpacedDiffusion, get_named_beta_schedule
+    d = GaussianSpacedDiffusion(use_timesteps=range(1000), betas=get_named_beta_schedule("linear", 1000), model_var_type="fixed_small")
+    A, B, C1, C2, sig = d.step_tables("ddim", 0.0)
+    assert float(sig.abs().max()) == 0.0
+    sp, sq = np.sqrt(d.alphas_cumprod_prev), np.sqrt(1.0 - d.alphas_cumprod_prev)
+    assert th.equal(C1, th.from_numpy(sp - sq / d.sqrt_recipm1_alphas_cumprod).float())
+    *_, sig1 = d.step_tables("ddim", 1.0)
+    assert th.allclose(sig1[1:] ** 2, th.from_numpy(d.posterior_variance).float()[1:], rtol=1e-4)
+
+
+def test_inpaint_blend_slices_own_their_memory():
+    """InpaintBlend clones its inputs (refreshing a cached plan must not write through to the caller's tensors)
+    and `slice` hands every sub-chain an independent copy of its clips."""
+    from gesture_b200.diffusion import InpaintBlend
+    seed, masks = th.randn(4, 6, 3), th.ones(4, 6, 1)
+    b = InpaintBlend(seed, masks, 0.5, 2, 6)
+    b.seed.zero_()
+    assert seed.abs().sum() > 0
+    b = InpaintBlend(seed, masks, 0.5, 2, 6)
+    s = b.slice(1, 3)
+    assert th.equal(s.seed, seed[1:3]) and s.mask.shape == (2, 6) and th.equal(s.factor, b.factor)
+    s.seed.zero_()
+    assert th.equal(b.seed, seed)
+
+
+def test_sub_chain_count_policy(monkeypatch):
+    from gesture_b200 import engine
+
+    class M:
+        pass
+    m = M()
+    monkeypatch.delenv("GD_SUBCHAINS", raising=False)
+    assert engine.sub_chain_count(m, (128, 123, 40), "ddpm") == 1        # auto: splitting is off (measured: no gain)
+    m.sub_chains = 4
+    assert engine.sub_chain_count(m, (128, 123, 40), "ddpm") == 4
+    assert engine.sub_chain_count(m, (3, 123, 40), "ddpm") == 3          # never more parts than clips
+    monkeypatch.setenv("GD_SUBCHAINS", "2")
+    assert engine.sub_chain_count(m, (128, 123, 40), "ddpm") == 2
