@@ -232,12 +232,12 @@ def kernel_breakdown(chain):
 
 def ncu_gemm_traffic(workload):
     """DRAM bytes per GEMM launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu launch list of one
-    denoise step of this workload (profiles/r01_launch_summary_v9_*.txt); None if there is no capture for it."""
-    name = {"tedexp-ours": "tedexp256", "beat-ours": "beat1024x40"}.get(workload)
+    denoise step of this workload (profiles/r02_launch_summary_*.txt); None if there is no capture for it."""
+    name = {"tedexp-ours": "tedexp256", "beat-ours": "beat1024"}.get(workload)
     if name is None:
         return None
     try:
-        for line in open(os.path.join(ROOT, "profiles", f"r01_launch_summary_v9_{name}.txt")):
+        for line in open(os.path.join(ROOT, "profiles", f"r02_launch_summary_{name}.txt")):
             f = [v.strip() for v in line.split("|")]
             if len(f) >= 5 and f[0] == "gemm":
                 return float(f[4]) * 1e6 / float(f[1])
@@ -487,7 +487,7 @@ def run_b200(args):
     total_flops = sum(a["flops"] for a in agg.values())
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel" + (" + gemm_resid_ln_kernel" if "gemm_ln" in agg else "") + " (tcgen05+TMA)", "achieved": ach, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": ncu_gemm_traffic(args.workload),
-                "traffic_note": "average DRAM bytes per GEMM launch, ncu launch list of one step (profiles/r01_launch_summary_v9_*.txt); "
+                "traffic_note": "average DRAM bytes per GEMM launch, ncu launch list of one step (profiles/r02_launch_summary_*.txt); "
                                 "algorithmic bytes per launch = %.0f" % (gm["bytes"] / gm["launches"]),
                 "peak_source": peak_src,
                 "launches_per_step": gm["launches"], "share_of_step": gm["ms"] / step_ms,

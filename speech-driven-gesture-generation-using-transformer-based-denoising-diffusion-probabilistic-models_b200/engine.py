@@ -258,6 +258,7 @@ class SamplingChain:
         self.native_encoder_chunk = int(env("GD_SPEECH_CHUNK", getattr(model, "native_encoder_chunk", 128)))
         self.graph = None
         self.graph_info = {}
+        self.py_denoise = None
         self._plan_key = None
         self.Tm = None
 
@@ -561,9 +562,14 @@ class SamplingChain:
         (N,C,T) is the Inpaint model's loop-invariant offset of the denoiser input (model.py:161-165).  `rng_consumed`:
         the caller (SplitChain) has already drawn this chain's share of the reference's per-step random numbers."""
         from .diffusion import InpaintBlend
+        # Any other callable (gaussian_diffusion.py:256-257 accepts arbitrary `denoise_fn`) cannot run inside a captured
+        # graph: the chain then steps eagerly - the denoiser still on the kernels, eps through a plain final projection, the
+        # update as the reference's own elementwise torch ops around the Python call (step_eager_callable).
+        self.py_denoise = None
         if denoise_fn is not None and not isinstance(denoise_fn, InpaintBlend):
-            raise NotImplementedError("denoise_fn must be an InpaintBlend (the fused in-paint epilogue); "
-                                      "arbitrary Python closures cannot run inside the captured chain")
+            if not callable(denoise_fn):
+                raise TypeError("denoise_fn must be callable")
+            self.py_denoise, denoise_fn = denoise_fn, None
         if tuple(x_T.shape) != (self.N, self.C, self.T):
             raise ValueError(f"noise shape {tuple(x_T.shape)} != {(self.N, self.C, self.T)}")
         assert wav.dim() == 2 and wav.shape[0] == self.N, f"Wav dim should be (N,T). Got: {tuple(wav.shape)}"
@@ -644,6 +650,32 @@ class SamplingChain:
         if cur > 0:
             main.wait_stream(self.side)
 
+    def step_eager_callable(self):
+        """One denoise step with an arbitrary Python `denoise_fn` between pred_x_start and the posterior mean
+        (p_mean_variance, gaussian_diffusion.py:252-259): every kernel of the plan except the fused projection+update, a plain
+        final projection to eps, then the update as torch elementwise ops in the reference's order."""
+        W, d, Mx = self.W, self.W.d, self.N * self.T
+        if getattr(self, "_eps_rows", None) is None or self._eps_rows.shape[0] != Mx:
+            self._eps_rows = th.empty(Mx, _POSE_PAD, device=self.device)
+            xn = self._buffers[1]
+            self._proj_op = self.L.linear(xn[:Mx], W.out_w, Mx, _POSE_PAD, d, bias=W.out_b, out_f32=self._eps_rows)
+        for op in self.plan[:-2]:  # (the concurrent lanes run back to back here)
+            op()
+        self._proj_op()
+        i = int(self.step.item())
+        A, B, C1, C2, sig = (t[i] for t in self.tabs)
+        eps = self._eps_rows.view(self.N, self.T, _POSE_PAD)[:, :, :self.C].transpose(1, 2).contiguous()
+        x = self.x
+        raw = A * x - B * eps
+        x0 = self.py_denoise(raw.clone())
+        mean = C1 * x0 + C2 * x
+        z = self.tape[i] if (self.tape is not None and i != 0) else None
+        new_x = mean + sig * z if z is not None else mean + 0.0
+        self.eps.copy_(eps); self.raw_x0.copy_(raw); self.x0.copy_(x0); self.mean.copy_(mean)
+        self.x.copy_(new_x)
+        self._pack_pose_rows()
+        self.step.fill_(i - 1)
+
     def set_state(self, x, i):
         """Teacher forcing: overwrite the sample and the loop index (parity harness)."""
         self.x.copy_(x.to(self.device).float())
@@ -708,6 +740,11 @@ class SamplingChain:
     def run(self, progress=False, n_steps=None):
         """Run the remaining chain (or `n_steps` steps). Returns the last step's dict."""
         total = self.n_steps if n_steps is None else n_steps
+        if self.py_denoise is not None:
+            for _ in range(total):
+                self.step_eager_callable()
+            self._pos += total
+            return self._result(max(self.n_steps - self._pos, 0))
         self.aux_step.fill_(max(self.n_steps - self._pos - total, 0))  # only the last step of this run hands back its dict
         if self.use_graph:
             self._ensure_graph()
@@ -727,7 +764,10 @@ class SamplingChain:
     def iterate(self, progress=False):
         """Progressive form (p_sample_loop_progressive): yields cloned per-step dicts."""
         for i in range(self.n_steps - 1, -1, -1):
-            self.step_eager()
+            if self.py_denoise is not None:
+                self.step_eager_callable()
+            else:
+                self.step_eager()
             self._pos += 1
             yield {k: v.clone() for k, v in self._result(i).items()}
 
@@ -765,6 +805,8 @@ class SplitChain:
 
     def begin(self, x_T, wav, denoise_fn=None, noise_tape=None, need_tape=True, input_offset=None):
         dev, n = self.device, self.n_steps
+        if denoise_fn is not None and not hasattr(denoise_fn, "slice"):
+            raise NotImplementedError("a Python denoise_fn needs the single (eager) chain: set model.sub_chains = 1")
         if need_tape and noise_tape is None:
             # the same draws, in the same order, as the single chain (one (N,C,T) normal_() per step, loop order)
             noise_tape = th.empty(n, self.N, self.C, self.T, device=dev)

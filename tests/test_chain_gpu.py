@@ -266,3 +266,31 @@ def test_layernorm_prologue_plan_is_bit_identical_to_default_plan(name, N):
                                                                 progress=False, noise_tape=tape).clone())
     assert th.isfinite(outs[1]).all()
     assert th.equal(outs[0], outs[1]), f"rel-L2 {rel_l2(outs[1], outs[0]):.3e}"
+
+
+@pytest.mark.parametrize("alg", ["ddpm", "ddim"])
+def test_python_denoise_fn_callable_matches_fused_blend(alg):
+    """An arbitrary Python `denoise_fn` (gaussian_diffusion.py:256-257) runs on the eager path - denoiser on the kernels, the
+    update as torch ops around the call.  With the in-paint closure written as a plain Python function it must reproduce the
+    fused InpaintBlend epilogue bit for bit (same eps, same rounding order)."""
+    from gesture_b200.diffusion import InpaintBlend
+    N = 3
+    model, diffusion, C, T, L, params = build("beat", "boost", respacing="ddim10", device="cuda")
+    wav = synthetic_wav(N, L, seed=61)
+    x_T, tape = noise_tape((N, C, T), 10, seed=62)
+    seed = th.randn(N, T, C, generator=th.Generator().manual_seed(63))
+    masks = th.ones(N, T, 1)
+    masks[:, 8:] = 0
+    blend = InpaintBlend(seed.cuda(), masks.cuda(), 0.6, 8, T)
+    loop = diffusion.p_sample_loop if alg == "ddpm" else diffusion.ddim_sample_loop
+    kw = {"noise_tape": tape} if alg == "ddpm" else {}
+    fused = {k: v.clone() for k, v in loop(model, (N, C, T), noise=x_T, model_kwargs={"wav": wav}, denoise_fn=blend, device="cuda", **kw).items()}
+    calls = []
+
+    def closure(x0):  # what generator.py:265-280 builds
+        calls.append(1)
+        return blend(x0)
+    eager = loop(model, (N, C, T), noise=x_T, model_kwargs={"wav": wav}, denoise_fn=closure, device="cuda", **kw)
+    assert len(calls) == 10
+    for k in ("sample", "pred_x_start", "raw_x_start", "eps"):
+        assert th.equal(fused[k], eager[k]), k
