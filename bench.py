@@ -59,6 +59,7 @@ def parse():
                     help="denoise steps captured per CUDA graph (0 = the whole chain as one graph, the default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ingraph", action="store_true", help="skip the CUPTI in-graph per-class breakdown")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling object (beat-1024 / beat-4x-512 over N ranks)")
     return ap.parse_args()
 
@@ -457,6 +458,15 @@ def run_b200(args):
                "h2d_bytes_per_step": wav_host.numel() * 4 + x_host.numel() * 4, "d2h_bytes_per_step": clips * T * C * 4}
 
     agg_pre = kernel_breakdown(chain) if rank == 0 else None
+    ingraph = None
+    if rank == 0 and not args.no_ingraph:
+        # the same kernels as they run INSIDE a graph (CUPTI records of one 10-step replay), next to the eager breakdown
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "profiles"))
+            from ingraph_breakdown import measure
+            ingraph = measure(model, diffusion, shape, wav_dev, x_T, graph_steps=10)
+        except Exception as exc:  # profiler unavailable on this box: say so instead of failing the bench
+            ingraph = {"unavailable": repr(exc)[:200]}
     plan_len, _flops_pre, speech_impl = len(chain.plan), sum(op.flops for op in chain.plan), chain.speech_impl
     graph_info = dict(chain.graph_info)
     strong = None
@@ -528,7 +538,7 @@ def run_b200(args):
             "kernel_breakdown_note": "eager step, one CUDA event between consecutive launches: a LOWER bound on the in-graph rates "
                                      "(the graph runs the step faster: no event gaps, concurrent branches overlap); in-graph per-class "
                                      "times from CUPTI are in profiles/r02_ingraph_breakdown_*.json",
-            "strong": strong, "cpu_baseline": cpu}
+            "ingraph_breakdown": ingraph, "strong": strong, "cpu_baseline": cpu}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
