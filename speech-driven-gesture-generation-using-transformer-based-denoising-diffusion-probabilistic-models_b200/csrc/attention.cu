@@ -377,7 +377,7 @@ __device__ __forceinline__ void conv_unit16_bf16(const uint8_t* src, uint8_t* ds
     }
 }
 
-template <int DK, int KB, int MAXT, int MAXREG, bool CONV_BF16>
+template <int DK, int KB, int MAXT, int MAXREG, bool CONV_BF16, bool TAIL_SPLIT>
 __global__ void __launch_bounds__(MAXT) __maxnreg__(MAXREG)
 dconv_attention_tma_kernel(const __grid_constant__ CUtensorMap tm_q0, const __grid_constant__ CUtensorMap tm_q1,
                            const __grid_constant__ CUtensorMap tm_k0, const __grid_constant__ CUtensorMap tm_k1,
@@ -395,6 +395,7 @@ dconv_attention_tma_kernel(const __grid_constant__ CUtensorMap tm_q0, const __gr
     uint8_t* cv_v = smem + geo.cv_v_off;
     float* s_taps = reinterpret_cast<float*>(smem + geo.taps_off);  // [3][CPH][w0 8 | w1 8 | w2 8 | b 8]
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + geo.bar_off);
+    float* tail_stats = reinterpret_cast<float*>(smem + geo.bar_off + 16);  // [4 partial tasks][16 rows][max, sum]
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int warp = tid >> 5, lane = tid & 31;
 
@@ -479,8 +480,7 @@ dconv_attention_tma_kernel(const __grid_constant__ CUtensorMap tm_q0, const __gr
         if (tid == 0 && item + n_stages * (int)gridDim.x < geo.n_items) issue_load(item + n_stages * gridDim.x, stage);
 
         // ---- attention core: one task = (head of the group, 16-query tile)
-        for (int task = warp; task < HG * q_tiles; task += (nthr >> 5)) {
-            const int hh = task / q_tiles, qt = task - hh * q_tiles;
+        auto run_tile = [&](const int hh, const int qt) {
             const int hc = hh * CPH;
             float s[KB * 2][4];
 #pragma unroll
@@ -563,6 +563,139 @@ dconv_attention_tma_kernel(const __grid_constant__ CUtensorMap tm_q0, const __gr
                         *reinterpret_cast<uint32_t*>(orow + col + n * 8) = pack_bf16x2(o[n][2 * half] * inv, o[n][2 * half + 1] * inv);
                 }
             }
+        };
+        // The same tile restricted to `nkb` (<= PKB) 16-key blocks starting at block kb_lo: a partial task of the split tail
+        // below.  Its normalised bf16 rows go into warp `sub`'s own (finished) Q tile of cv_q, the row statistics next to the
+        // barriers; 128-B rows with the 16-byte chunks XOR-swizzled by the row, so the quad store pattern spreads over the banks.
+        constexpr int PKB = (KB + 3) / 4;
+        auto run_partial = [&](const int qt, const int kb_lo, const int nkb, const int sub) {
+            float s[PKB * 2][4];
+#pragma unroll
+            for (int n = 0; n < PKB * 2; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+            const uint32_t qaddr = qrow_u + qt * 16 * ATT2_ROW_BYTES;
+#pragma unroll
+            for (int kk = 0; kk < DK / 16; ++kk) {
+                uint32_t a0, a1, a2, a3;
+                ldsm_x4(qaddr + (((kk * 2 + (lane >> 4)) ^ sw) << 4), a0, a1, a2, a3);
+                const uint32_t kaddr = krow_u + (((kk * 2 + ((lane >> 3) & 1)) ^ sw) << 4) + kb_lo * 16 * ATT2_ROW_BYTES;
+#pragma unroll
+                for (int j = 0; j < PKB; ++j) {
+                    if (j >= nkb) continue;  // warp-uniform
+                    uint32_t b0, b1, b2, b3;
+                    ldsm_x4(kaddr + j * 16 * ATT2_ROW_BYTES, b0, b1, b2, b3);
+                    mma_bf16_16816(s[2 * j], a0, a1, a2, a3, b0, b1);
+                    mma_bf16_16816(s[2 * j + 1], a0, a1, a2, a3, b2, b3);
+                }
+            }
+            float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+            for (int n = 0; n < PKB * 2; ++n) {
+                if (n >= 2 * nkb) continue;
+                const int j = (kb_lo * 2 + n) * 8 + 2 * t;  // key index of s[n][0]
+                if (j >= Lk) s[n][0] = s[n][2] = -INFINITY;
+                if (j + 1 >= Lk) s[n][1] = s[n][3] = -INFINITY;
+                m0 = fmaxf(m0, fmaxf(s[n][0], s[n][1]));
+                m1 = fmaxf(m1, fmaxf(s[n][2], s[n][3]));
+            }
+            m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+            m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+            m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+            m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+            const float o0 = m0 * scale_log2, o1 = m1 * scale_log2;
+            float sum0 = 0.f, sum1 = 0.f;
+            uint32_t pk[PKB * 2][2];
+#pragma unroll
+            for (int n = 0; n < PKB * 2; ++n) {
+                pk[n][0] = pk[n][1] = 0u;
+                if (n >= 2 * nkb) continue;
+                const float e0 = ex2_approx(fmaf(s[n][0], scale_log2, -o0));
+                const float e1 = ex2_approx(fmaf(s[n][1], scale_log2, -o0));
+                const float e2 = ex2_approx(fmaf(s[n][2], scale_log2, -o1));
+                const float e3 = ex2_approx(fmaf(s[n][3], scale_log2, -o1));
+                sum0 += e0 + e1;
+                sum1 += e2 + e3;
+                pk[n][0] = pack_bf16x2(e0, e1);
+                pk[n][1] = pack_bf16x2(e2, e3);
+            }
+            sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+            sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+            sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+            sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+            float o[DK / 8][4];
+#pragma unroll
+            for (int n = 0; n < DK / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+            for (int j = 0; j < PKB; ++j) {
+                if (j >= nkb) continue;
+#pragma unroll
+                for (int nb = 0; nb < DK / 16; ++nb) {
+                    uint32_t b0, b1, b2, b3;
+                    ldsm_x4_trans(vrow_u + (((nb * 2 + (lane >> 4)) ^ sw) << 4) + (kb_lo + j) * 16 * ATT2_ROW_BYTES, b0, b1, b2, b3);
+                    mma_bf16_16816(o[2 * nb], pk[2 * j][0], pk[2 * j][1], pk[2 * j + 1][0], pk[2 * j + 1][1], b0, b1);
+                    mma_bf16_16816(o[2 * nb + 1], pk[2 * j][0], pk[2 * j][1], pk[2 * j + 1][0], pk[2 * j + 1][1], b2, b3);
+                }
+            }
+            const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+            uint8_t* part = cv_q + sub * 16 * ATT2_ROW_BYTES;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int r = g + half * 8;
+                const float inv = half ? inv1 : inv0;
+#pragma unroll
+                for (int n = 0; n < DK / 8; ++n)
+                    *reinterpret_cast<uint32_t*>(part + r * ATT2_ROW_BYTES + ((n ^ (r & 7)) << 4) + 4 * t) =
+                        pack_bf16x2(o[n][2 * half] * inv, o[n][2 * half + 1] * inv);
+                if (t == 0) {
+                    tail_stats[(sub * 16 + r) * 2] = half ? m1 : m0;
+                    tail_stats[(sub * 16 + r) * 2 + 1] = half ? sum1 : sum0;
+                }
+            }
+        };
+        const int n_warps = nthr >> 5, n_tasks = HG * q_tiles;
+        // One task more than warps (the 138-token joint attention of tedexp: nine 16-query tiles on eight warps): the last tile
+        // would keep one warp busy for a whole extra round while seven wait at the barrier (25 % of the kernel's stall samples,
+        // profiles/r02_ncu_attention_full.txt).  It is split by KEY ranges over four warps instead and the four partial
+        // softmax results are merged (each warp merges 16 of the 64 output columns).
+        const bool split_tail = TAIL_SPLIT && HG == 1 && KB >= 4 && n_tasks == n_warps + 1 && n_warps >= 4;
+        for (int task = warp; task < (split_tail ? n_warps : n_tasks); task += n_warps) run_tile(task / q_tiles, task % q_tiles);
+        if (split_tail && warp < 4) {
+            const int qt = q_tiles - 1;
+            run_partial(qt, (warp * KB) / 4, ((warp + 1) * KB) / 4 - (warp * KB) / 4, warp);
+            asm volatile("bar.sync 1, 128;\n" ::: "memory");  // warps 0..3: partial rows and statistics are in shared memory
+            const int r = lane & 15, h = lane >> 4;
+            float mx = -INFINITY, ms[4], ls[4];
+#pragma unroll
+            for (int sidx = 0; sidx < 4; ++sidx) {
+                ms[sidx] = tail_stats[(sidx * 16 + r) * 2];
+                ls[sidx] = tail_stats[(sidx * 16 + r) * 2 + 1];
+                mx = fmaxf(mx, ms[sidx]);
+            }
+            float wsum = 0.f, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int sidx = 0; sidx < 4; ++sidx) {
+                const float w = ls[sidx] * ex2_approx((ms[sidx] - mx) * scale_log2);
+                wsum += w;
+                const uint4 u = *reinterpret_cast<const uint4*>(cv_q + (sidx * 16 + r) * ATT2_ROW_BYTES + (((2 * warp + h) ^ (r & 7)) << 4));
+                const uint32_t wd[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    acc[2 * e] = fmaf(w, __uint_as_float(wd[e] << 16), acc[2 * e]);
+                    acc[2 * e + 1] = fmaf(w, __uint_as_float(wd[e] & 0xffff0000u), acc[2 * e + 1]);
+                }
+            }
+            const int i = qt * 16 + r;
+            if (i < Lq && (i < p.q_rows[0] || p.out[1])) {
+                __nv_bfloat16* orow = (i < p.q_rows[0])
+                                          ? p.out[0] + ((size_t)clip * p.q_rows[0] + i) * p.out_ld[0]
+                                          : p.out[1] + ((size_t)clip * p.q_rows[1] + (i - p.q_rows[0])) * p.out_ld[1];
+                const float inv = 1.0f / wsum;
+                uint4 o4;
+                o4.x = pack_bf16x2(acc[0] * inv, acc[1] * inv);
+                o4.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
+                o4.z = pack_bf16x2(acc[4] * inv, acc[5] * inv);
+                o4.w = pack_bf16x2(acc[6] * inv, acc[7] * inv);
+                *reinterpret_cast<uint4*>(orow + grp * 64 + warp * 16 + h * 8) = o4;
+            }
         }
         __syncthreads();  // cv may be overwritten by the next item's conv
     }
@@ -598,7 +731,14 @@ static int launch_attention_tma(const AttnParams& p, int n_clips, cudaStream_t s
     // warps fighting for the same issue slots cost more than the idle round.)
     constexpr int MAXT = 256;
     constexpr int MAXREG = KB <= 5 ? 96 : 128;  // short key ranges need fewer registers: 20 instead of 16 warps per SM
-    auto kern = dconv_attention_tma_kernel<DK, KB, MAXT, MAXREG, CONV_BF16>;
+    // Split tail (one 16-query tile more than warps): OFF by default.  Measured on B200 in the tedexp chain (GD_ATTN_TAIL=1,
+    // profiles/r02_ab_attention_tail_split.jsonl): 5.25-5.28 vs 5.13-5.15 ms/step - slower.  The warps that wait at the barrier
+    // while one warp finishes the ninth tile are not lost time: the second resident CTA uses the issue slots, and the merge
+    // plus 116 bytes of spill cost more than the idle round.  Same conclusion as the 9-warp variant.
+    constexpr bool TAIL = (DK == 64 && KB >= 4);
+    static const bool tail_on = getenv("GD_ATTN_TAIL") && getenv("GD_ATTN_TAIL")[0] == '1';
+    auto kern = (TAIL && tail_on) ? dconv_attention_tma_kernel<DK, KB, MAXT, MAXREG, CONV_BF16, TAIL>
+                                  : dconv_attention_tma_kernel<DK, KB, MAXT, MAXREG, CONV_BF16, false>;
     const int Lq_pad = (p.Lq + 15) & ~15, Lk_pad = KB * 16;
     Attn2Geom geo{};
     geo.groups = p.heads / HG;
@@ -618,7 +758,7 @@ static int launch_attention_tma(const AttnParams& p, int n_clips, cudaStream_t s
     geo.taps_off = geo.cv_v_off + Lk_pad * ATT2_ROW_BYTES;
     geo.bar_off = geo.taps_off + 3 * DK * 4 * (int)sizeof(float);
     geo.tx_bytes = (uint32_t)(p.Lq + 2 * p.Lk) * ATT2_ROW_BYTES;
-    const size_t smem = (size_t)geo.bar_off + 16 + 128 /*base alignment slack*/;
+    const size_t smem = (size_t)geo.bar_off + 16 + 512 /*tail-split row statistics*/ + 128 /*base alignment slack*/;
     CUtensorMap tq[2], tk[2], tv[2];
     for (int sgi = 0; sgi < 2; ++sgi) {
         const int has_q = p.q_rows[sgi] > 0, has_k = p.kv_rows[sgi] > 0;
