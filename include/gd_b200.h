@@ -138,6 +138,11 @@ int gd_linear_ddpm(const gd_linear_desc* d, const gd_ddpm_desc* u, void* stream)
  * ------------------------------------------------------------------------------------------ */
 int gd_layernorm(const float* x, int32_t ldx, const float* gamma, const float* beta, void* out_bf16, int32_t ldo,
                  int32_t M, int32_t D, float eps, void* stream);
+/* ABI 4: the same with a second parameter set for rows >= split_row (gamma2 / beta2 may be NULL = one set): the tedexp joint
+ * attention updates pose rows and memory rows in one GEMM, and they feed norm_ff / norm_ff_mem (models/nn.py:116-123). */
+int gd_layernorm_split(const float* x, int32_t ldx, const float* gamma, const float* beta, const float* gamma2,
+                       const float* beta2, int32_t split_row, void* out_bf16, int32_t ldo, int32_t M, int32_t D, float eps,
+                       void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * gd_linear_resid_ln: residual GEMM with the LayerNorm that follows it fused into the epilogue:

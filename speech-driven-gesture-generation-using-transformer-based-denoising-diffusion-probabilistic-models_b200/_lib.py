@@ -65,6 +65,7 @@ SYMBOLS = {
     "gd_linear_resid_ln": (c_i32, [C.POINTER(LinearDesc), C.POINTER(LnDesc), c_vp]),
     "gd_linear_ln_bf16": (c_i32, [C.POINTER(LinearDesc), c_vp, c_vp, c_f32, c_vp]),
     "gd_layernorm": (c_i32, [c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_f32, c_vp]),
+    "gd_layernorm_split": (c_i32, [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_f32, c_vp]),
     "gd_dconv_attention": (c_i32, [C.POINTER(AttnDesc), c_vp]),
     "gd_dconv_attention_f32in": (c_i32, [C.POINTER(AttnDesc), c_vp]),
     "gd_scatter_step_row_f32": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),

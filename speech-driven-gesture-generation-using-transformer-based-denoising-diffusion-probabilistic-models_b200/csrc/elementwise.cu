@@ -16,7 +16,8 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
                                                              const float* __restrict__ gamma,
                                                              const float* __restrict__ beta,
                                                              __nv_bfloat16* __restrict__ out, int ldo, int M,
-                                                             float eps) {
+                                                             float eps, const float* __restrict__ gamma2,
+                                                             const float* __restrict__ beta2, int split_row) {
     pdl_launch_dependents();
     pdl_wait();
     constexpr int V = D / 128;  // float4 chunks per lane and row
@@ -32,13 +33,15 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
 #pragma unroll
         for (int i = 0; i < V; ++i) v[r][i] = __ldcg(xr + i * 32 + lane);  // L2-coherent: see common.cuh (PDL and L1)
     }
-    const float4* g4 = reinterpret_cast<const float4*>(gamma);
-    const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         float mean, rstd;
         ln_row_stats<V>(v[r], eps, mean, rstd);
         if (row0 + r < M) {
+            // rows >= split_row take the second parameter set (tedexp: pose rows -> norm_ff, memory rows -> norm_ff_mem)
+            const bool second = gamma2 != nullptr && row0 + r >= split_row;
+            const float4* g4 = reinterpret_cast<const float4*>(second ? gamma2 : gamma);
+            const float4* b4 = reinterpret_cast<const float4*>(second ? beta2 : beta);
             uint2* orow = reinterpret_cast<uint2*>(out + (size_t)(row0 + r) * ldo);
 #pragma unroll
             for (int i = 0; i < V; ++i)
@@ -192,10 +195,21 @@ static inline int grid_for(size_t total, int block) {
 
 using namespace gd;
 
+extern "C" int gd_layernorm_split(const float* x, int32_t ldx, const float* gamma, const float* beta, const float* gamma2,
+                                  const float* beta2, int32_t split_row, void* out_bf16, int32_t ldo, int32_t M, int32_t D,
+                                  float eps, void* stream);
+
 extern "C" int gd_layernorm(const float* x, int32_t ldx, const float* gamma, const float* beta, void* out_bf16,
                             int32_t ldo, int32_t M, int32_t D, float eps, void* stream) {
+    return gd_layernorm_split(x, ldx, gamma, beta, nullptr, nullptr, 0, out_bf16, ldo, M, D, eps, stream);
+}
+
+extern "C" int gd_layernorm_split(const float* x, int32_t ldx, const float* gamma, const float* beta, const float* gamma2,
+                                  const float* beta2, int32_t split_row, void* out_bf16, int32_t ldo, int32_t M, int32_t D,
+                                  float eps, void* stream) {
     gd::KindScope kind_scope("ln");
     if (!x || !gamma || !beta || !out_bf16) return set_error(GD_ERR_INVALID, "gd_layernorm: null pointer");
+    if ((gamma2 == nullptr) != (beta2 == nullptr)) return set_error(GD_ERR_INVALID, "gd_layernorm_split: gamma2 / beta2 go together");
     if (M <= 0) return set_error(GD_ERR_INVALID, "gd_layernorm: M <= 0");
     if (ldx % 4 || ldo % 4 || ldx < D || ldo < D) return set_error(GD_ERR_INVALID, "gd_layernorm: bad row stride");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -203,13 +217,13 @@ extern "C" int gd_layernorm(const float* x, int32_t ldx, const float* gamma, con
     const int wpb = 8, grid = (M + wpb * R - 1) / (wpb * R);
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
     if (D == 256) {
-        GD_CUDA_CHECK(launch_k(layernorm_rows_kernel<256, R>, grid, wpb * 32, 0, s, 1, x, ldx, gamma, beta, o, ldo, M, eps));
+        GD_CUDA_CHECK(launch_k(layernorm_rows_kernel<256, R>, grid, wpb * 32, 0, s, 1, x, ldx, gamma, beta, o, ldo, M, eps, gamma2, beta2, split_row));
     } else if (D == 512) {
-        GD_CUDA_CHECK(launch_k(layernorm_rows_kernel<512, R>, grid, wpb * 32, 0, s, 1, x, ldx, gamma, beta, o, ldo, M, eps));
+        GD_CUDA_CHECK(launch_k(layernorm_rows_kernel<512, R>, grid, wpb * 32, 0, s, 1, x, ldx, gamma, beta, o, ldo, M, eps, gamma2, beta2, split_row));
     } else if (D == 128) {
-        GD_CUDA_CHECK(launch_k(layernorm_rows_kernel<128, R>, grid, wpb * 32, 0, s, 1, x, ldx, gamma, beta, o, ldo, M, eps));
+        GD_CUDA_CHECK(launch_k(layernorm_rows_kernel<128, R>, grid, wpb * 32, 0, s, 1, x, ldx, gamma, beta, o, ldo, M, eps, gamma2, beta2, split_row));
     } else if (D == 1024) {
-        GD_CUDA_CHECK(launch_k(layernorm_rows_kernel<1024, R>, grid, wpb * 32, 0, s, 1, x, ldx, gamma, beta, o, ldo, M, eps));
+        GD_CUDA_CHECK(launch_k(layernorm_rows_kernel<1024, R>, grid, wpb * 32, 0, s, 1, x, ldx, gamma, beta, o, ldo, M, eps, gamma2, beta2, split_row));
     } else {
         return set_error(GD_ERR_INVALID, "gd_layernorm: D=%d unsupported (128/256/512/1024)", D);
     }

@@ -169,10 +169,12 @@ class _Launcher:
         return Op(lambda: gd.check(lib.gd_linear_ln_bf16(C.byref(d), _p(g), _p(b), 1e-5, self.stream()), "gd_linear_ln_bf16"),
                   "gemm", 2 * M * N * K, nbytes)
 
-    def layernorm(self, x, gamma_beta, out, M, D):
+    def layernorm(self, x, gamma_beta, out, M, D, second=None, split=0):
+        """LayerNorm rows; rows >= `split` use the parameter pair `second` when given (one launch for two streams)."""
         lib, g, b = self.lib, gamma_beta[0], gamma_beta[1]
-        args = (_p(x), x.stride(0), _p(g), _p(b), _p(out), out.stride(0), M, D, 1e-5)
-        return Op(lambda: gd.check(lib.gd_layernorm(*args, self.stream()), "gd_layernorm"), "layernorm", 8 * M * D, 6 * M * D)
+        g2, b2 = (second[0], second[1]) if second is not None else (None, None)
+        args = (_p(x), x.stride(0), _p(g), _p(b), _p(g2), _p(b2), split, _p(out), out.stride(0), M, D, 1e-5)
+        return Op(lambda: gd.check(lib.gd_layernorm_split(*args, self.stream()), "gd_layernorm"), "layernorm", 8 * M * D, 6 * M * D)
 
     def attention(self, n_clips, heads, d_k, q, k, v, out, taps, f32in):
         """q/k/v/out: lists of up to two (tensor_view, rows_per_clip) segments; views start at the right column."""
@@ -248,6 +250,9 @@ class SamplingChain:
         # last one (out_layers.0).  bf16 plans only (the fp32-activation parity path keeps fp32 Q|K|V rows).
         self.ln_prologue = bool(int(env("GD_LN_PROLOGUE", int(ln_prologue)))) and not self.f32act \
             and not self.fuse_ln
+        # tedexp: hoist LayerNorm + Q|K|V of the layer-0 memory self-attention out of the loop (bf16 plans; GD_HOIST_MEM0=0: off)
+        self.hoist_mem0 = bool(int(env("GD_HOIST_MEM0", int(getattr(model, "hoist_mem0", True))))) and not self.f32act \
+            and not self.fuse_ln and not self.ln_prologue
         self.encoder_chunk = getattr(model, "encoder_chunk", 16)
         # once-per-clip speech encoder: "native" = ResNetSE-34 on our tensor-core convolutions in split precision (bf16x3:
         # fp32-class products), "native-bf16" = the same with plain bf16 feature maps (faster, ~1e-2 feature error that a
@@ -328,7 +333,23 @@ class SamplingChain:
             mem_init[:, 1:] = emb.view(N, Ts, d)
             mem_tab = th.empty(n, d, device=dev)
             self.L.linear(zt, W.embm_w, n, d, d, bias=W.embm_b, rowbias=W.pe, period=1, offset=self.T, out_f32=mem_tab)()
-            return {"Tm": Tm, "mem_init": mem_init.view(N * Tm, d), "mem_tab": mem_tab}
+            cond = {"Tm": Tm, "mem_init": mem_init.view(N * Tm, d), "mem_tab": mem_tab}
+            if self.hoist_mem0:
+                # Layer 0 of the memory stream starts every step from the same rows (only row 0, the timestep token, moves):
+                # LayerNorm + fused Q|K|V of the memory self-attention of layer 0 (nn.py:101-103) are evaluated ONCE per chain
+                # for the 103 speech rows and once per timestep for row 0 ([n_steps, 3d] table, scattered per step).  Row-wise
+                # kernels, so the values are bit-identical to recomputing them in every step.
+                ly = W.layers[0]
+                xn0 = th.empty(N * Tm, d, device=dev, dtype=th.bfloat16)
+                self.L.layernorm(cond["mem_init"], ly["ln_sam"], xn0, N * Tm, d)()
+                qkv0 = th.empty(N * Tm, 3 * d, device=dev, dtype=th.bfloat16)
+                self.L.linear(xn0, ly["sam"]["wqkv"], N * Tm, 3 * d, d, bias=ly["sam"]["bqkv"], out_bf16=qkv0)()
+                xnt = th.empty(n, d, device=dev, dtype=th.bfloat16)
+                self.L.layernorm(mem_tab, ly["ln_sam"], xnt, n, d)()
+                qkv0_tab = th.empty(n, 3 * d, device=dev, dtype=th.bfloat16)
+                self.L.linear(xnt, ly["sam"]["wqkv"], n, 3 * d, d, bias=ly["sam"]["bqkv"], out_bf16=qkv0_tab)()
+                cond["qkv0"], cond["qkv0_tab"] = qkv0, qkv0_tab
+            return cond
         # oneway: memory = [z_t ; blend(low|mid|high)] -> emb_mem + PE[0..Tm)  (model.py:90-115, nn.py:218-219)
         longest = max(z_low.shape[1], z_mid.shape[1], z_high.shape[1])
         pad = lambda z: th.nn.functional.pad(z, (0, 0, longest - z.shape[1], 0))  # noqa: E731  zero rows in front
@@ -399,9 +420,8 @@ class SamplingChain:
         if ln is not None:
             if ln2 is None or split >= M:
                 ops.append(L.layernorm(H, ln, xn, M, d))
-            else:
-                ops.append(L.layernorm(H[:split], ln, xn[:split], split, d))
-                ops.append(L.layernorm(H[split:], ln2, xn[split:], M - split, d))
+            else:  # pose rows and memory rows in ONE launch, each with its own gamma / beta
+                ops.append(L.layernorm(H, ln, xn, M, d, second=ln2, split=split))
 
     def _ffn_block(self, ops, f, lo, hi, xn, hid, H, next_ln=None, ln_in=None):
         """xn rows [lo,hi) already hold LN(H): up-projection + ReLU², down-projection + residual (+ the next LayerNorm).
@@ -459,8 +479,9 @@ class SamplingChain:
             if not self.ln_prologue:
                 ops.append(L.layernorm(X, W.layers[0]["ln_sa"], xn[:Mx], Mx, d))
                 tag(len(ops) - 1, region, 0)
-                ops.append(L.layernorm(Mem, W.layers[0]["ln_sam"], xn[Mx:], Mm, d))
-                tag(len(ops) - 1, region, 1)
+                if "qkv0" not in cond:
+                    ops.append(L.layernorm(Mem, W.layers[0]["ln_sam"], xn[Mx:], Mm, d))
+                    tag(len(ops) - 1, region, 1)
             for li, ly in enumerate(W.layers):
                 last = li == W.n_layers - 1
                 nxt = None if last else W.layers[li + 1]
@@ -470,7 +491,18 @@ class SamplingChain:
                 tag(s0, region, 0)
                 s0 = len(ops)
                 L.sm_cap = cap1
-                self._attn_block(ops, ly["sam"], Mx, R, [(Mx, Tm)], xn, qkv, ao, H, heads, next_ln=ly["ln_ca"], ln_in=ly["ln_sam"])
+                if li == 0 and "qkv0" in cond:
+                    # layer 0: Q|K|V of the memory rows come from the per-chain buffer; only row 0 of every clip is per step
+                    q0, w3 = cond["qkv0"], 3 * d
+                    a_q0 = (_p(q0), _p(cond["qkv0_tab"]), _p(self.step), N, Tm, 0, w3, w3)
+                    ops.append(Op(lambda: gd.check(lib.gd_scatter_step_row_bf16(*a_q0, L.stream()), "gd_scatter_step_row_bf16"),
+                                  "scatter", 0, 4 * N * w3))
+                    a0 = ly["sam"]
+                    ops.append(L.attention(N, heads, d // heads, [(q0[:, 0:], Tm)], [(q0[:, d:], Tm)], [(q0[:, 2 * d:], Tm)],
+                                           [(ao[Mx:], Tm)], a0["taps"], False))
+                    self._resid(ops, ao[Mx:R], a0["wo"], a0["bo"], Mm, d, H[Mx:R], ly["ln_ca"], xn[Mx:R])
+                else:
+                    self._attn_block(ops, ly["sam"], Mx, R, [(Mx, Tm)], xn, qkv, ao, H, heads, next_ln=ly["ln_ca"], ln_in=ly["ln_sam"])
                 tag(s0, region, 1)
                 L.sm_cap = 0
                 region += 1

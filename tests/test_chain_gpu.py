@@ -294,3 +294,29 @@ def test_python_denoise_fn_callable_matches_fused_blend(alg):
     assert len(calls) == 10
     for k in ("sample", "pred_x_start", "raw_x_start", "eps"):
         assert th.equal(fused[k], eager[k]), k
+
+
+def test_layer0_memory_qkv_hoist_is_bit_identical():
+    """tedexp: LayerNorm + Q|K|V of the layer-0 memory self-attention evaluated once per chain (+ a per-timestep row-0 table)
+    instead of in every step - row-wise kernels, so the poses must not change by a bit (N = 3 and a multi-tile N = 40)."""
+    from gesture_b200.engine import release_chains
+    from gesture_b200.generator import Generator
+    for N in (3, 40):
+        model, diffusion, C, T, L, params = build("tedexp", "boost", respacing="ddim20", device="cuda")
+        wav = synthetic_wav(N, L, seed=81)
+        x_T, tape = noise_tape((N, C, T), 20, seed=82)
+        outs = []
+        for flag in (False, True):
+            model.hoist_mem0 = flag
+            release_chains(model)
+            outs.append(Generator(model, diffusion).generate_sample((N, C, T), wav, noise=x_T, sample_alg="ddpm", device="cuda",
+                                                                    progress=False, noise_tape=tape).clone())
+        # second chain on the cached plan (buffers refreshed in place) with other speech
+        wav2 = synthetic_wav(N, L, seed=83)
+        again = Generator(model, diffusion).generate_sample((N, C, T), wav2, noise=x_T, sample_alg="ddpm", device="cuda",
+                                                            progress=False, noise_tape=tape).clone()
+        model.hoist_mem0 = False
+        release_chains(model)
+        ref2 = Generator(model, diffusion).generate_sample((N, C, T), wav2, noise=x_T, sample_alg="ddpm", device="cuda",
+                                                           progress=False, noise_tape=tape)
+        assert th.equal(outs[0], outs[1]) and th.equal(again, ref2)
