@@ -212,9 +212,29 @@ __device__ __forceinline__ void epilogue_conv_chunk(const GemmParams& p, size_t 
 // outputs share one 32-bit element offset per column (off0 + j*T); AUX / INPAINT are compile-time so the common
 // sampling step carries no dead predicates (the first version spent ~94 instructions per element, mostly on 64-bit
 // index arithmetic and per-element pointer tests).
-template <bool AUX, bool INPAINT>
+// x and the step's noise of one 32-column chunk, issued BEFORE the warp waits for the accumulator (they do not depend on it):
+// the two HBM round trips of the update then overlap the tile's TMA loads and MMAs instead of following them.
+__device__ __forceinline__ void ddpm_prefetch_chunk(const GemmParams& p, const float* tape_t, int row, int col0, float (&xv)[32],
+                                                    float (&zv)[32]) {
+    const gd_ddpm_desc& u = p.ddpm;
+    const int T = u.T;
+    const int clip = row / T;
+    const uint32_t off0 = static_cast<uint32_t>((clip * u.C + col0) * T + (row - clip * T));
+    const int ncol = u.C - col0;
+    const float* const xp = u.x + off0;
+    const float* const zp = tape_t ? tape_t + off0 : nullptr;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const bool ok = j < ncol;
+        xv[j] = ok ? __ldcg(xp + j * T) : 0.f;
+        zv[j] = (ok && zp) ? __ldg(zp + j * T) : 0.f;
+    }
+}
+
+template <bool AUX, bool INPAINT, bool PRE = false>
 __device__ __forceinline__ void epilogue_ddpm_chunk(const GemmParams& p, const DdpmStepCoefs& cf, const float* tape_t,
-                                                    int row, int col0, const uint32_t (&v)[32]) {
+                                                    int row, int col0, const uint32_t (&v)[32], const float* xpre = nullptr,
+                                                    const float* zpre = nullptr) {
     const gd_ddpm_desc& u = p.ddpm;
     const int T = u.T;
     const int clip = row / T;
@@ -243,8 +263,13 @@ __device__ __forceinline__ void epilogue_ddpm_chunk(const GemmParams& p, const D
         for (int i = 0; i < 16; ++i) {
             const int j = h * 16 + i;
             const bool ok = j < ncol;
-            xv[i] = ok ? __ldcg(xp + j * T) : 0.f;
-            zv[i] = (ok && zp) ? __ldg(zp + j * T) : 0.f;
+            if (PRE) {
+                xv[i] = xpre[j];
+                zv[i] = zpre[j];
+            } else {
+                xv[i] = ok ? __ldcg(xp + j * T) : 0.f;
+                zv[i] = (ok && zp) ? __ldg(zp + j * T) : 0.f;
+            }
         }
         float xn[16];
 #pragma unroll
@@ -472,10 +497,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int n0 = (tile % n_tiles) * BN;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            mbar_wait(&acc_full_bar[acc], acc_phase);
-            tc_fence_after_sync();
             const int row0 = m0 + quad * 32;
             const int row = row0 + lane;
+            constexpr bool DDPM_PRE = (MODE == MODE_DDPM && BN == 64);  // one 32-column chunk per warp and tile
+            float xpre[DDPM_PRE ? 32 : 1], zpre[DDPM_PRE ? 32 : 1];
+            if constexpr (DDPM_PRE) {
+                if (row < p.M && !ddpm_aux && !ddpm_inpaint) ddpm_prefetch_chunk(p, tape_t, row, n0 + half * (BN / 2), xpre, zpre);
+            }
+            mbar_wait(&acc_full_bar[acc], acc_phase);
+            tc_fence_after_sync();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * WCOLS;
             // the accumulator stage goes back to the MMA issuer as soon as this warp's last TMEM load has landed in
             // registers - not after the stores - so tile i+2 can start while tile i is still being written out
@@ -630,6 +660,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                 epilogue_ddpm_chunk<true, true>(p, cf, tape_t, row, col0, v);
                             else if (ddpm_aux)
                                 epilogue_ddpm_chunk<true, false>(p, cf, tape_t, row, col0, v);
+                            else if constexpr (DDPM_PRE)
+                                epilogue_ddpm_chunk<false, false, true>(p, cf, tape_t, row, col0, v, xpre, zpre);
                             else
                                 epilogue_ddpm_chunk<false, false>(p, cf, tape_t, row, col0, v);
                         } else
