@@ -264,6 +264,8 @@ class SamplingChain:
         self.graph = None
         self.graph_info = {}
         self.py_denoise = None
+        self._plans = {}  # parked plans by key (see begin)
+        self._use_tape = True
         self._plan_key = None
         self.Tm = None
 
@@ -377,7 +379,7 @@ class SamplingChain:
     def _ddpm_desc(self):
         u = gd.DdpmDesc()
         u.x = _p(self.x)
-        u.noise_tape = _p(self.tape)
+        u.noise_tape = _p(self.tape) if getattr(self, "_use_tape", True) else None
         u.coef_A, u.coef_B, u.coef_C1, u.coef_C2, u.sigma = [_p(t) for t in self.tabs]
         u.step_ptr = _p(self.step)
         u.n_clips, u.C, u.T = self.N, self.C, self.T
@@ -639,15 +641,24 @@ class SamplingChain:
             self.xa_add.copy_(input_offset.float())
         elif self.xa_add is not None:
             self.xa_add = None
+        # A plan (launch list + descriptors + activation buffers + captured graph) is specific to the memory length, to whether
+        # the in-paint blend / the noise tape / the input offset are wired into the update epilogue, and to the tape and offset
+        # buffers it points at.  Plans are kept side by side: generate_sequence goes window 0 (no blend) -> window 1
+        # (blend) -> ..., eval code alternates sampling and teacher-forced steps; each plan is built and captured once.
         key = (cond["Tm"], blend_key, need_tape, _p(self.tape) if need_tape else 0, _p(self.xa_add))
-        if self.plan is None or key != self._plan_key:
+        if self._plan_key is not None and key != self._plan_key:  # park the active plan
+            self._plans[self._plan_key] = (self.plan, self.graph, self.graph_info, self._buffers, self._ddpm, self.blend, self.Tm)
+        st = self._plans.pop(key, None) if key != self._plan_key else None
+        if self.plan is None or (key != self._plan_key and st is None):
             self.blend = denoise_fn
             self.Tm = cond["Tm"]
-            if not need_tape:
-                self.tape = None
+            self._use_tape = need_tape
             self.plan = self._build_plan(cond)
-            self._plan_key, self.graph = key, None
+            self._plan_key, self.graph, self.graph_info = key, None, {}
         else:
+            if st is not None:
+                self.plan, self.graph, self.graph_info, self._buffers, self._ddpm, self.blend, self.Tm = st
+                self._plan_key = key
             # same plan/graph: refresh the buffers the captured kernels read
             old = self._buffers[5]
             for name, val in cond.items():
@@ -657,6 +668,9 @@ class SamplingChain:
                 self.blend.seed.copy_(denoise_fn.seed)
                 self.blend.mask.copy_(denoise_fn.mask)
                 self.blend.factor.copy_(denoise_fn.factor)
+        self._eps_rows = None  # (the eager Python-denoise_fn projection is bound to the active plan's buffers)
+        while len(self._plans) > 3:  # bounded: the oldest parked plan goes
+            self._plans.pop(next(iter(self._plans)))
         self.x.copy_(x_T.float())
         self._pack_pose_rows()
         self.step.fill_(self.n_steps - 1)

@@ -320,3 +320,29 @@ def test_layer0_memory_qkv_hoist_is_bit_identical():
         ref2 = Generator(model, diffusion).generate_sample((N, C, T), wav2, noise=x_T, sample_alg="ddpm", device="cuda",
                                                            progress=False, noise_tape=tape)
         assert th.equal(outs[0], outs[1]) and th.equal(again, ref2)
+
+
+def test_plans_are_kept_side_by_side(monkeypatch):
+    """toggling the in-paint blend (generate_sequence: window 0 without, windows 1.. with) must not rebuild the
+    plan and re-capture the graph every time - the two plans live side by side; results stay bit-identical."""
+    from gesture_b200 import engine
+    from gesture_b200.generator import Generator
+    N = 2
+    model, diffusion, C, T, L, params = build("beat", "boost", respacing="ddim20", device="cuda")
+    gen = Generator(model, diffusion)
+    wav = synthetic_wav(N, L, seed=91)
+    x_T, tape = noise_tape((N, C, T), 20, seed=92)
+    seedp = th.randn(N, T, C, generator=th.Generator().manual_seed(93))
+    masks = th.ones(N, T, 1)
+    masks[:, 10:] = 0
+    builds = []
+    real = engine.SamplingChain._build_plan
+    monkeypatch.setattr(engine.SamplingChain, "_build_plan", lambda self, cond: (builds.append(1), real(self, cond))[1])
+    plain = dict(noise=x_T, sample_alg="ddpm", device="cuda", progress=False, noise_tape=tape)
+    blend = dict(plain, inpaint_poses=seedp, inpaint_masks=masks, trans_factor=0.575, pose_seed_len=10)
+    a1 = gen.generate_sample((N, C, T), wav, **plain).clone()
+    b1 = gen.generate_sample((N, C, T), wav, **blend).clone()
+    a2 = gen.generate_sample((N, C, T), wav, **plain).clone()
+    b2 = gen.generate_sample((N, C, T), wav, **blend).clone()
+    assert len(builds) == 2, builds
+    assert th.equal(a1, a2) and th.equal(b1, b2) and not th.equal(a1, b1)
