@@ -834,8 +834,12 @@ extern "C" int gd_linear_bf16(const gd_linear_desc* d, void* stream) {
         }
     }
     // Widest tile that still gives every SM work; narrow tiles when the problem is small.
-    const int bn = (d->N % 256 == 0 && m_tiles * (d->N / 256) >= sm_count()) ? 256
-                   : (d->N % 128 == 0 && m_tiles * (d->N / 128) >= sm_count()) ? 128 : 64;
+    int bn = (d->N % 256 == 0 && m_tiles * (d->N / 256) >= sm_count()) ? 256
+             : (d->N % 128 == 0 && m_tiles * (d->N / 128) >= sm_count()) ? 128 : 64;
+    {  // GD_GEMM_BN=128|64 caps the tile width (A/B runs: wave quantisation against per-tile efficiency)
+        static const int bn_cap = getenv("GD_GEMM_BN") ? atoi(getenv("GD_GEMM_BN")) : 0;
+        if (bn_cap >= 64 && bn > bn_cap) bn = bn_cap;
+    }
 #define GD_LAUNCH(BN_)                                                                                   \
     (mode == MODE_TMA_BF16  ? launch_gemm<BN_, MODE_TMA_BF16>(p, d->A, d->lda, d->W, d->ldw, s)          \
      : mode == MODE_TMA_F32 ? launch_gemm<BN_, MODE_TMA_F32>(p, d->A, d->lda, d->W, d->ldw, s)           \
