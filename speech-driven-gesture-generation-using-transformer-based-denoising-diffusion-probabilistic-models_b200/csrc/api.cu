@@ -114,6 +114,21 @@ int validate_ddpm(const gd_ddpm_desc* u) {
 
 }  // namespace gd
 
+#ifdef GD_TRACE
+namespace gd {
+void set_trace_gemm(unsigned long long* buf);
+void set_trace_elementwise(unsigned long long* buf);
+void set_trace_attention(unsigned long long* buf);
+}  // namespace gd
+// profiling builds only: buf[0] = slot counter, buf[1] = capacity, slots of 10 words from buf[16]
+extern "C" int gd_debug_set_trace(void* buf) {
+    gd::set_trace_gemm(static_cast<unsigned long long*>(buf));
+    gd::set_trace_elementwise(static_cast<unsigned long long*>(buf));
+    gd::set_trace_attention(static_cast<unsigned long long*>(buf));
+    return cudaDeviceSynchronize() == cudaSuccess ? GD_OK : GD_ERR_CUDA;
+}
+#endif
+
 extern "C" int gd_abi_version(void) { return GD_ABI_VERSION; }
 extern "C" const char* gd_last_error(void) { return gd::g_err; }
 extern "C" uint64_t gd_launch_count(void) { return gd::g_launches.load(std::memory_order_relaxed); }

@@ -417,8 +417,11 @@ dconv_attention_tma_kernel(const __grid_constant__ CUtensorMap tm_q0, const __gr
     }
     for (int i = tid; i < geo.raw_bytes / 16; i += nthr) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();  // the zero fill is ordered before the TMA writes that follow the barrier
+    const int trace_slot = tid == 0 ? GD_TRACE_OPEN(500) : -1;
+    GD_TRACE_MARK(trace_slot, 1);  // prologue (zero fill, taps) done
     pdl_launch_dependents();
     pdl_wait();  // set-up above touched only weights and shared memory; Q/K/V come from the previous kernel
+    GD_TRACE_MARK(trace_slot, 2);
     __syncthreads();
 
     auto issue_load = [&](int item, int stage) {  // one thread; token rows start at raw row 1 of the stage's blocks
@@ -463,6 +466,7 @@ dconv_attention_tma_kernel(const __grid_constant__ CUtensorMap tm_q0, const __gr
         const uint8_t* raw_k = raw_q + geo.raw_k_off;
         const uint8_t* raw_v = raw_q + geo.raw_v_off;
         mbar_wait(&full_bar[stage], phase);
+        if (k_iter == 0) GD_TRACE_MARK(trace_slot, 3);  // first item's rows landed
         // ---- depth-wise conv3 over tokens: raw -> cv, one unit = 16 tokens x 4 columns, no boundary predicates
         for (int it = tid; it < conv_items; it += nthr) {
             const int hc4 = it & 15, sg = it >> 4;  // 8-byte column group within the 128-B row, 16-row segment
@@ -699,6 +703,7 @@ dconv_attention_tma_kernel(const __grid_constant__ CUtensorMap tm_q0, const __gr
         }
         __syncthreads();  // cv may be overwritten by the next item's conv
     }
+    GD_TRACE_MARK(trace_slot, 8);
 }
 
 int make_rows_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
@@ -872,6 +877,10 @@ static int run_attention(const gd_attn_desc* d, bool fp32_in, void* stream) {
     if (d->d_k == 64) return fp32_in ? dispatch_kb<float, 64>(p, d->n_clips, s) : dispatch_kb<__nv_bfloat16, 64>(p, d->n_clips, s);
     return set_error(GD_ERR_INVALID, "gd_dconv_attention: d_k=%d unsupported (32/64)", d->d_k);
 }
+
+#ifdef GD_TRACE
+void set_trace_attention(unsigned long long* buf) { cudaMemcpyToSymbol(t_trace_buf, &buf, sizeof(buf)); }
+#endif
 
 }  // namespace gd
 

@@ -21,6 +21,24 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_trace():
+    """Profiling build with in-kernel %globaltimer stamps (-DGD_TRACE) -> libgd_b200_trace.so next to the product library;
+    loaded through GD_LIB by profiles/kernel_timeline.py only."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    out = os.path.join(os.path.dirname(HERE), "libgd_b200_trace.so")
+    obj_dir = os.path.join(HERE, "_obj_trace")
+    os.makedirs(obj_dir, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, src[:-3] + ".o")
+        subprocess.run([nvcc] + FLAGS + ["-DGD_TRACE", "-c", os.path.join(HERE, src), "-o", obj], check=True, cwd=HERE)
+        return obj
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs + ["-lcudart"], check=True, cwd=HERE)
+    return out
+
+
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
@@ -40,4 +58,7 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--trace" in sys.argv:
+        print(build_trace())
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

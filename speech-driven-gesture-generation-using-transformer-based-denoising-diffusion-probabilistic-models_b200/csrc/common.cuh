@@ -30,6 +30,37 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\
 __device__ __forceinline__ int load_step(const int* step_ptr) { return __ldcg(step_ptr); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 
+// ---------------------------------------------------------------- in-kernel timeline (profiling builds only: -DGD_TRACE)
+// Block 0 of every traced launch takes the next 10-word slot of a global buffer and stamps %globaltimer at fixed points of the
+// kernel; profiles/kernel_timeline.py turns the slots into the serial path of a denoise step (where a small kernel's
+// microseconds go: waiting for its predecessor, the first TMA round trip, MMA, epilogue, drain).  The product library is built
+// without GD_TRACE: the macros vanish.
+#ifdef GD_TRACE
+static __device__ unsigned long long* t_trace_buf = nullptr;  // per translation unit; set by gd_debug_set_trace
+__device__ __forceinline__ unsigned long long trace_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ int trace_open(int kind) {  // one thread of block 0
+    unsigned long long* b = t_trace_buf;
+    if (!b || blockIdx.x != 0) return -1;
+    const int cap = static_cast<int>(b[1]);
+    const int slot = static_cast<int>(atomicAdd(b, 1ull));
+    if (slot >= cap) return -1;
+    b[16 + slot * 10 + 9] = static_cast<unsigned long long>(kind);
+    return slot;
+}
+__device__ __forceinline__ void trace_mark(int slot, int idx) {
+    if (slot >= 0) t_trace_buf[16 + slot * 10 + idx] = trace_now();
+}
+#define GD_TRACE_OPEN(kind) trace_open(kind)
+#define GD_TRACE_MARK(slot, idx) trace_mark(slot, idx)
+#else
+#define GD_TRACE_OPEN(kind) (-1)
+#define GD_TRACE_MARK(slot, idx) ((void)(slot))
+#endif
+
 // ---------------------------------------------------------------- clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;

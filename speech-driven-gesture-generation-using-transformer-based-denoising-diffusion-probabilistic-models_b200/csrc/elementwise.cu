@@ -18,8 +18,11 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
                                                              __nv_bfloat16* __restrict__ out, int ldo, int M,
                                                              float eps, const float* __restrict__ gamma2,
                                                              const float* __restrict__ beta2, int split_row) {
+    const int trace_slot = threadIdx.x == 0 ? GD_TRACE_OPEN(200) : -1;
+    GD_TRACE_MARK(trace_slot, 0);
     pdl_launch_dependents();
     pdl_wait();
+    GD_TRACE_MARK(trace_slot, 2);
     constexpr int V = D / 128;  // float4 chunks per lane and row
     // a warp owns R consecutive rows and issues all their loads before the first reduction (more bytes in flight per warp)
     const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
@@ -48,6 +51,7 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
                 orow[i * 32 + lane] = ln_apply_pack(v[r][i], mean, rstd, __ldg(g4 + i * 32 + lane), __ldg(b4 + i * 32 + lane));
         }
     }
+    GD_TRACE_MARK(trace_slot, 8);
 }
 
 // ------------------------------------------------------------------------------- DDPM update
@@ -132,8 +136,11 @@ __global__ void __launch_bounds__(256) scatter_row_bf16_kernel(__nv_bfloat16* __
                                                                const __nv_bfloat16* __restrict__ table,
                                                                const int* __restrict__ step_ptr, int n_clips,
                                                                int rows_per_clip, int row_index, int width, int ld) {
+    const int trace_slot = threadIdx.x == 0 ? GD_TRACE_OPEN(300) : -1;
+    GD_TRACE_MARK(trace_slot, 0);
     pdl_launch_dependents();
     pdl_wait();
+    GD_TRACE_MARK(trace_slot, 2);
     const int t = load_step(step_ptr);
     const int w8 = width >> 3;
     const uint4* trow = reinterpret_cast<const uint4*>(table + (size_t)t * width);
@@ -180,9 +187,13 @@ __global__ void __launch_bounds__(256) cast_rows_bf16_kernel(const float* __rest
 }
 
 __global__ void step_add_kernel(int* step_ptr, int delta) {
+    const int trace_slot = GD_TRACE_OPEN(400);
+    GD_TRACE_MARK(trace_slot, 0);
     pdl_launch_dependents();
     pdl_wait();
+    GD_TRACE_MARK(trace_slot, 2);
     *step_ptr = load_step(step_ptr) + delta;
+    GD_TRACE_MARK(trace_slot, 8);
 }
 
 static inline int grid_for(size_t total, int block) {
@@ -190,6 +201,10 @@ static inline int grid_for(size_t total, int block) {
     const size_t cap = (size_t)sm_count() * 16;
     return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
+
+#ifdef GD_TRACE
+void set_trace_elementwise(unsigned long long* buf) { cudaMemcpyToSymbol(t_trace_buf, &buf, sizeof(buf)); }
+#endif
 
 }  // namespace gd
 

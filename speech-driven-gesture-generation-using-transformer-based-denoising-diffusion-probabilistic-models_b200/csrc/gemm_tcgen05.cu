@@ -364,12 +364,27 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         else
             tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
     }
+#ifdef GD_TRACE
+    __shared__ int trace_slot_s;
+    if (threadIdx.x == 0) {
+        trace_slot_s = GD_TRACE_OPEN(100 + MODE);
+        GD_TRACE_MARK(trace_slot_s, 0);  // entry (before barrier init / TMEM allocation complete)
+    }
+#endif
     tc_fence_before_sync();
     __syncthreads();
     if (CL > 1) cluster_sync_all();  // the peer's barriers and TMEM exist before any cross-CTA traffic
     tc_fence_after_sync();
+#ifdef GD_TRACE
+    const int trace_slot = trace_slot_s;
+    if (threadIdx.x == 0) GD_TRACE_MARK(trace_slot, 1);  // prologue done
+#else
+    const int trace_slot = -1;
+    (void)trace_slot;
+#endif
     pdl_launch_dependents();
     pdl_wait();  // operands and outputs belong to the chain: nothing below may run before the previous kernel is done
+    if (threadIdx.x == 0) GD_TRACE_MARK(trace_slot, 2);  // predecessor complete
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
@@ -426,6 +441,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after_sync();
+                    if (it == 0 && kb == 0) GD_TRACE_MARK(trace_slot, 3);  // first operands landed
                     if constexpr (NB == 2) {
                         // operand reuse: every (A, B) product of the stage from tiles that were loaded once
                         constexpr int NPAIR = NA + 1;  // S1: (A,B0) (A,B1);  S2: (hi,Whi) (lo,Whi) (hi,Wlo)
@@ -464,6 +480,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     umma_commit(&acc_full_bar[acc]);
                 else
                     umma_commit_pair(&acc_full_bar[acc], 0b11);
+                GD_TRACE_MARK(trace_slot, 4);  // MMAs of the (last) tile issued
             }
         }
     } else if (warp >= 4) {
@@ -506,6 +523,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             mbar_wait(&acc_full_bar[acc], acc_phase);
             tc_fence_after_sync();
+            if (ew == 0 && lane == 0) GD_TRACE_MARK(trace_slot, 5);  // accumulator of the (last) tile complete
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * WCOLS;
             // the accumulator stage goes back to the MMA issuer as soon as this warp's last TMEM load has landed in
             // registers - not after the stores - so tile i+2 can start while tile i is still being written out
@@ -672,11 +690,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             }
         }
+        if (ew == 0 && lane == 0) GD_TRACE_MARK(trace_slot, 6);  // last store issued
         if ((MODE == MODE_TMA_BF16 || MODE == MODE_TMA_F32) && lane == 0) bulk_wait_group0();
+        if (ew == 0 && lane == 0) GD_TRACE_MARK(trace_slot, 7);  // stores drained
     }
 
     tc_fence_before_sync();
     __syncthreads();
+    if (threadIdx.x == 0) GD_TRACE_MARK(trace_slot, 8);  // exit
     if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer can still multicast into it / arrive on its barriers
     if (warp == 2) {
         if (CL == 1)
@@ -796,6 +817,10 @@ static int validate_linear(const gd_linear_desc* d) {
         return set_error(GD_ERR_INVALID, "gd_linear: A/W must be 16-byte aligned");
     return GD_OK;
 }
+
+#ifdef GD_TRACE
+void set_trace_gemm(unsigned long long* buf) { cudaMemcpyToSymbol(t_trace_buf, &buf, sizeof(buf)); }
+#endif
 
 }  // namespace gd
 
