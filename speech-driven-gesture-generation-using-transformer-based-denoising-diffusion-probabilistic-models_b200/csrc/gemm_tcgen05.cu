@@ -315,6 +315,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
     constexpr bool IS_CONV = MODE >= MODE_CONV;
+    constexpr bool PREFETCH_W = (CL == 1) && !IS_CONV;  // single-CTA tiles of the Linear layers
     constexpr int NA = (MODE == MODE_CONV_S2) ? 2 : 1, NB = (MODE >= MODE_CONV_S1) ? 2 : 1;
     using Cfg = GemmCfg<BN, CL, NA, NB, (MODE == MODE_TMA_F32) ? GD_F32_STAGING : 4096>;
     constexpr int STAGES = Cfg::STAGES;
@@ -383,7 +384,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     (void)trace_slot;
 #endif
     pdl_launch_dependents();
-    pdl_wait();  // operands and outputs belong to the chain: nothing below may run before the previous kernel is done
+    // W is a weight matrix: it does not depend on the previous kernel of the chain, so the producer puts the W tiles of its first
+    // pipeline stages in flight BEFORE it waits for that kernel (the CTA is resident and idle for 2-7 us at small batches,
+    // profiles/r02_kernel_timeline_*.json); after the wait only the activation tiles remain to be fetched for those stages.
+    int w_preissued = 0;
+    if (PREFETCH_W && warp == 0 && lane == 0) {
+        for (int tile = cluster_id; tile < num_tiles && w_preissued < STAGES; tile += num_clusters) {
+            const int n0 = (tile % n_tiles) * BN;
+            for (int kb = 0; kb < k_blocks && w_preissued < STAGES; ++kb, ++w_preissued) {
+                mbar_arrive_expect_tx(&full_bar[w_preissued], Cfg::STAGE_BYTES);
+                tma_load_2d(smem_b + w_preissued * Cfg::B_BYTES, &tmap_b, &full_bar[w_preissued], kb * BLOCK_K, n0);
+            }
+        }
+    }
+    pdl_wait();  // activations and outputs belong to the chain: nothing below may touch them before the previous kernel is done
     if (threadIdx.x == 0) GD_TRACE_MARK(trace_slot, 2);  // predecessor complete
     const uint32_t tmem_base = *tmem_slot;
 
@@ -391,10 +405,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            int issued = 0;  // pipeline stages filled so far; the first `w_preissued` already have their W tile in flight
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 const int m0 = GD_TILE_M0(tile);
                 const int n0 = (tile % n_tiles) * BN;
-                for (int kb = 0; kb < k_blocks; ++kb) {
+                for (int kb = 0; kb < k_blocks; ++kb, ++issued) {
+                    if (PREFETCH_W && issued < w_preissued) {  // first pass over the ring: slot free, W on its way, A missing
+                        tma_load_2d(smem_a + stage * NA * Cfg::A_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K, m0);
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                        continue;
+                    }
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (CL == 1) {
                         mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
