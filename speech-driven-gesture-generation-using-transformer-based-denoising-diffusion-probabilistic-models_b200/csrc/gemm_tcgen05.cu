@@ -884,6 +884,22 @@ extern "C" int gd_linear_bf16(const gd_linear_desc* d, void* stream) {
     // Widest tile that still gives every SM work; narrow tiles when the problem is small.
     int bn = (d->N % 256 == 0 && m_tiles * (d->N / 256) >= sm_count()) ? 256
              : (d->N % 128 == 0 && m_tiles * (d->N / 128) >= sm_count()) ? 128 : 64;
+    {
+        // Small problems (at most half a wave of m-tiles: the strong-scaling regime) are bound by the operand bytes the busiest
+        // CTA has to pull from L2, not by throughput (profiles/r02_kernel_timeline_beat128.json: ~100 GB/s per SM): pick the
+        // tile width that minimises rounds x (A tile + W tile) bytes; ties go to the wider tile.  GD_GEMM_SMALL=0: old rule.
+        static const bool small_rule = !(getenv("GD_GEMM_SMALL") && getenv("GD_GEMM_SMALL")[0] == '0');
+        if (small_rule && m_tiles * 2 <= sm_count()) {
+            long best = -1;
+            for (int cand = 256; cand >= 64; cand >>= 1) {
+                if (d->N % cand) continue;
+                const long tiles = (long)m_tiles * (d->N / cand);
+                const long rounds = (tiles + sm_count() - 1) / sm_count();
+                const long bytes = rounds * ((long)d->K * (BLOCK_M + cand) * 2);
+                if (best < 0 || bytes < best) best = bytes, bn = cand;
+            }
+        }
+    }
     {  // GD_GEMM_BN=128|64 caps the tile width (A/B runs: wave quantisation against per-tile efficiency)
         static const int bn_cap = getenv("GD_GEMM_BN") ? atoi(getenv("GD_GEMM_BN")) : 0;
         if (bn_cap >= 64 && bn > bn_cap) bn = bn_cap;
