@@ -885,11 +885,14 @@ extern "C" int gd_linear_bf16(const gd_linear_desc* d, void* stream) {
     int bn = (d->N % 256 == 0 && m_tiles * (d->N / 256) >= sm_count()) ? 256
              : (d->N % 128 == 0 && m_tiles * (d->N / 128) >= sm_count()) ? 128 : 64;
     {
-        // Small problems (at most half a wave of m-tiles: the strong-scaling regime) are bound by the operand bytes the busiest
-        // CTA has to pull from L2, not by throughput (profiles/r02_kernel_timeline_beat128.json: ~100 GB/s per SM): pick the
-        // tile width that minimises rounds x (A tile + W tile) bytes; ties go to the wider tile.  GD_GEMM_SMALL=0: old rule.
+        // Problems of up to two waves of m-tiles are bound by the operand bytes the busiest CTA has to pull from L2, not by
+        // throughput (profiles/r02_kernel_timeline_beat128.json: ~100 GB/s per SM): pick the tile width that minimises
+        // rounds x (A tile + W tile) bytes; ties go to the wider tile.  Measured (r02_ab_small_problem_tile_rule*.jsonl): beat 128
+        // clips -4.7 %, 256 clips -2.4 %, beat-4x 64 clips -1.4 %, tedexp 32 clips -2.5 %, larger batches unchanged (the rule
+        // then picks what the old one did).  GD_GEMM_SMALL=0: old rule; GD_GEMM_SMALL_M: m-tile limit.
         static const bool small_rule = !(getenv("GD_GEMM_SMALL") && getenv("GD_GEMM_SMALL")[0] == '0');
-        if (small_rule && m_tiles * 2 <= sm_count()) {
+        static const int small_max = getenv("GD_GEMM_SMALL_M") ? atoi(getenv("GD_GEMM_SMALL_M")) : sm_count() * 2;
+        if (small_rule && m_tiles <= small_max) {
             long best = -1;
             for (int cand = 256; cand >= 64; cand >>= 1) {
                 if (d->N % cand) continue;
