@@ -735,7 +735,9 @@ static int launch_attention_tma(const AttnParams& p, int n_clips, cudaStream_t s
     // of eight - was SLOWER in the chain: attention 1.45 -> 1.60 ms per tedexp step; 40 bytes of spill and 18 instead of 16
     // warps fighting for the same issue slots cost more than the idle round.)
     constexpr int MAXT = 256;
-    constexpr int MAXREG = KB <= 5 ? 96 : 128;  // short key ranges need fewer registers: 20 instead of 16 warps per SM
+    // short key ranges need fewer registers: 20 instead of 16 warps per SM; the beat windows (d_k = 32, <= 48 keys) compile to 80
+    // registers without spilling: four CTAs per SM instead of three (at 128 clips per GPU every CTA then has ONE item)
+    constexpr int MAXREG = (DK == 32 && KB <= 3) ? 80 : (KB <= 5 ? 96 : 128);
     // Split tail (one 16-query tile more than warps): OFF by default.  Measured on B200 in the tedexp chain (GD_ATTN_TAIL=1,
     // profiles/r02_ab_attention_tail_split.jsonl): 5.25-5.28 vs 5.13-5.15 ms/step - slower.  The warps that wait at the barrier
     // while one warp finishes the ninth tile are not lost time: the second resident CTA uses the issue slots, and the merge
